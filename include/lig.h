@@ -1,0 +1,197 @@
+/*
+ * lig.h — C ABI of the B200-native endpoint picker (drop-in for the ext-proc scheduler hot path).
+ *
+ * This is the boundary a cgo shim binds.  Every entry point below replaces a
+ * piece of the reference's Go scheduling package; the reference location is cited per symbol as
+ * <file>:<line> relative to the reference repository root (kubernetes-sigs/llm-instance-gateway
+ * @ 8e96339).  Plain pointers and sizes only: no C++ types, no torch types, no Go pointers kept
+ * after a call returns.
+ *
+ * Conventions
+ *   - every function returning int returns 0 on success or a negative LIG_ERR_* code; the
+ *     human-readable reason is available (thread-local) from lig_last_error();
+ *   - per-request outcomes are NOT errors: they are reported in lig_pick.status
+ *     (LIG_OK / LIG_DROP / LIG_EMPTY), mirroring Schedule()'s (pod, err) return;
+ *   - there is no CPU fallback anywhere behind this header: without a CUDA device lig_create
+ *     fails with LIG_ERR_CUDA.
+ */
+#ifndef LIG_H_
+#define LIG_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LIG_ABI_VERSION 1
+
+/* ---- per-request status (lig_pick.status) ------------------------------------------------------
+ * LIG_OK    Schedule returned a pod, nil                      pkg/ext-proc/scheduling/scheduler.go:120-121
+ * LIG_DROP  the "drop request" leaf fired: the Go side must return
+ *           status.Errorf(codes.ResourceExhausted, "dropping request due to limited backend
+ *           resources") wrapped like scheduler.go:117         scheduler.go:83-89  -> 429 at handlers/server.go:97-109
+ * LIG_EMPTY the tree returned ([], nil): "failed to apply filter, resulted 0 pods, this should
+ *           never happen"                                      scheduler.go:116-118
+ */
+enum { LIG_OK = 0, LIG_DROP = 1, LIG_EMPTY = 2 };
+
+/* ---- batch-level error codes (negative return values) ---------------------------------------- */
+enum {
+  LIG_ERR_INVALID     = -1, /* bad argument (null pointer, P/A/R out of the ctx capacity, ...)    */
+  LIG_ERR_CUDA        = -2, /* CUDA runtime/driver failure, or no device                          */
+  LIG_ERR_STALE_EPOCH = -3, /* the epoch passed to schedule is not a resident snapshot            */
+  LIG_ERR_NO_SNAPSHOT = -4, /* schedule called before any snapshot upload                         */
+  LIG_ERR_RANGE       = -5  /* a host value does not fit the device record (see lig_pack_pods)    */
+};
+
+/* ---- request descriptor: 16 bytes, one int4 load on the device --------------------------------
+ * Replaces scheduling.LLMRequest (pkg/ext-proc/scheduling/types.go:4-11).  The filter tree reads
+ * only ResolvedTargetModel and Critical (filter.go:163-181); Model and TargetModels are unused on
+ * the path.  ResolvedTargetModel is interned by the host layer into adapter_id: the index of the
+ * adapter's row in the snapshot bitmap, or any value outside [0, A) for a model that no pod
+ * lists in ActiveModels (the base model, or a never-loaded adapter) — such a request matches no
+ * pod in loRAAffinityPredicate, exactly like a Go map lookup miss (filter.go:170).
+ * rand_key keys the request's private random stream used for the final pick (see below).
+ */
+typedef struct lig_req {
+  int32_t  adapter_id;
+  uint32_t flags;      /* bit 0 = Critical (types.go:10); other bits must be 0 */
+  uint64_t rand_key;
+} lig_req;
+#define LIG_REQ_CRITICAL 1u
+
+/* ---- result: 8 bytes ---------------------------------------------------------------------------
+ * pod_idx      index into the snapshot's pod order (= order of the slice the injected
+ *              PodMetricsProvider returned at pack time, scheduler.go:108-115), -1 unless LIG_OK;
+ *              the host maps it back to backend.Pod{Name,Address} (backend/types.go:8-11).
+ * n_survivors  len(pods) after the filter tree (the argument of rand.Intn, scheduler.go:120).
+ */
+typedef struct lig_pick {
+  int32_t  pod_idx;
+  uint16_t status;
+  uint16_t n_survivors;
+} lig_pick;
+
+/* ---- thresholds: the compile-time constants of scheduler.go:15-24, made parameters so the
+ * reference's own predicate test (filter_test.go:304-338 uses (0, 0.8)) can be run on the GPU. */
+typedef struct lig_thresholds {
+  double  kv_cache_threshold;         /* kvCacheThreshold        = 0.8 */
+  int64_t queue_threshold_critical;   /* queueThresholdCritical  = 5   */
+  int64_t queueing_threshold_lora;    /* queueingThresholdLoRA   = 50  */
+} lig_thresholds;
+
+typedef struct lig_ctx lig_ctx; /* opaque; one per (process, device) */
+
+/* Hard limits of the device records. */
+#define LIG_MAX_PODS     32768   /* list entries and n_survivors are uint16 */
+#define LIG_MAX_ADAPTERS 65534
+
+/* ---- lifetime -------------------------------------------------------------------------------- */
+/* Replaces scheduling.NewScheduler (scheduler.go:93-99): binds the scheduler to one CUDA device
+ * and reserves HBM + pinned staging for snapshots of up to max_pods x max_adapters and host
+ * batches of up to max_batch requests (device-pointer batches are not limited by max_batch). */
+int  lig_create(lig_ctx** out, int device, int max_pods, int max_adapters, int max_batch);
+void lig_destroy(lig_ctx* ctx);
+
+int  lig_set_thresholds(lig_ctx* ctx, const lig_thresholds* t);   /* scheduler.go:15-24 */
+int  lig_get_thresholds(const lig_ctx* ctx, lig_thresholds* t);
+
+/* ---- snapshot = the value of PodMetricsProvider.AllPodMetrics() (scheduler.go:108-115,
+ * backend/provider.go:38-46) frozen at one refresh tick, in device layout -----------------------
+ *
+ * Packed blob, W = ceil(P/32), Ppad = 32*W, every section 16-byte aligned, in this order:
+ *   double   kv[Ppad]          Metrics.KVCacheUsagePercent           backend/types.go:24
+ *   int32_t  q[Ppad]           Metrics.WaitingQueueSize              backend/types.go:23
+ *   uint16_t n_active[Ppad]    len(Metrics.ActiveModels)             backend/types.go:19
+ *   uint16_t max_active[Ppad]  Metrics.MaxActiveModels (saturated)   backend/types.go:21
+ *   uint32_t bitmap[A][W]      bit (a, p) = adapter a in pod p's ActiveModels (adapter-major)
+ * Padding pods (index >= P) are ignored by every kernel.
+ */
+size_t lig_snapshot_bytes(int P, int A);
+
+/* Pure host helper (no GPU): narrow Go-width pod metrics to the device record.
+ *   q          must fit int32, else LIG_ERR_RANGE (never silently wrapped);
+ *   n_active   must be in [0, LIG_MAX_ADAPTERS], else LIG_ERR_RANGE;
+ *   max_active is saturated to [0, 65535]: canAcceptNewLoraPredicate (filter.go:175-177) is
+ *              `n_active < max_active` and n_active <= 65534, so saturation cannot change it. */
+int lig_pack_pods(int P, const int64_t* waiting_queue_size, const int64_t* n_active_models,
+                  const int64_t* max_active_models, int32_t* q_out, uint16_t* n_active_out,
+                  uint16_t* max_active_out);
+
+/* Pure host helper (no GPU): lay the five arrays out as the packed blob described above. */
+int lig_pack_snapshot(void* blob, int P, int A, const double* kv, const int32_t* q,
+                      const uint16_t* n_active, const uint16_t* max_active,
+                      const uint32_t* bitmap_adapter_major /* A x ceil(P/32) */);
+
+/* Upload a snapshot from host arrays and build the per-class survivor tables on the device.
+ * After it returns, `epoch` is resident; the previous epoch stays resident too (two slots), so
+ * in-flight batches against it still complete.  Replaces the per-request
+ * AllPodMetrics() materialisation of scheduler.go:114-115 by one pack per refresh tick. */
+int lig_upload_snapshot(lig_ctx* ctx, uint64_t epoch, int P, int A, const double* kv,
+                        const int32_t* q, const uint16_t* n_active, const uint16_t* max_active,
+                        const uint32_t* bitmap_adapter_major);
+
+/* Same, but the packed blob is already in HBM (e.g. the receive buffer of an NCCL broadcast of
+ * the snapshot).  The blob is copied into the ctx on `stream` (a cudaStream_t, may be NULL =
+ * legacy default stream); table build is enqueued on the same stream, nothing is synchronised. */
+int lig_upload_snapshot_device(lig_ctx* ctx, uint64_t epoch, int P, int A, const void* d_blob,
+                               void* stream);
+
+/* ---- the hot path ------------------------------------------------------------------------------
+ * Replaces R calls of Scheduler.Schedule (scheduler.go:113-122) == R walks of the defaultFilter
+ * tree (scheduler.go:26-91, filter.go:44-187) followed by rand.Intn(len(pods)).
+ *
+ * The random pick.  The reference draws from Go's auto-seeded global source, so its pick is not
+ * reproducible; this ABI defines it as what `rand.New(src).Intn(n)` returns (math/rand, Go 1.22:
+ * Intn -> Int31n; Int31() = Int63()>>32) when src is a SplitMix64 source private to the request:
+ *     state = seed ^ rand_key;
+ *     next(): state += 0x9E3779B97F4A7C15; z = state;
+ *             z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9; z = (z ^ (z >> 27)) * 0x94D049BB133111EB;
+ *             return z ^ (z >> 31);
+ *     Int63() = next() >> 1            (so Int31() = next() >> 33)
+ *     Int31n(n): if n is a power of two: Int31() & (n-1)
+ *                else max = 2^31 - 1 - (2^31 % n); v = Int31(); while (v > max) v = Int31();
+ *                     return v % n
+ * and pod_idx is the k-th survivor in ascending pod index (= slice order, pods[i] scheduler.go:121).
+ */
+
+/* Host buffers in, host buffers out: H2D copy, kernels, D2H copy, all inside the call
+ * (chunk-pipelined on the ctx's own streams); blocks until `out` is complete. */
+int lig_schedule_batch(lig_ctx* ctx, uint64_t epoch, uint64_t seed, const lig_req* reqs, int R,
+                       lig_pick* out);
+
+/* HBM-resident batch: d_reqs / d_out are device pointers (16-byte / 8-byte aligned); the work is
+ * enqueued on `stream` and NOT synchronised.  This is the class-table fast path. */
+int lig_schedule_batch_device(lig_ctx* ctx, uint64_t epoch, uint64_t seed, const lig_req* d_reqs,
+                              int R, lig_pick* d_out, void* stream);
+
+/* Direct scan: every request walks the whole tree over all P pods itself (one warp per request,
+ * no class tables).  d_masks, when not NULL, receives the survivor set of every request as
+ * R x ceil(P/32) words (bit p%32 of word p/32 = pod p survives) — the GPU analogue of
+ * Filter.Filter's return value (filter.go:12-15, 44-73), used by the parity tests. */
+int lig_schedule_scan_device(lig_ctx* ctx, uint64_t epoch, uint64_t seed, const lig_req* d_reqs,
+                             int R, lig_pick* d_out, uint32_t* d_masks, void* stream);
+
+/* Host-buffer wrapper of the direct scan (test hook; masks may be NULL). */
+int lig_schedule_scan(lig_ctx* ctx, uint64_t epoch, uint64_t seed, const lig_req* reqs, int R,
+                      lig_pick* out, uint32_t* masks);
+
+/* Read back one class table entry of a resident snapshot (test hook): the survivor list the
+ * fast path uses for requests (critical, adapter_id).  `list` must hold P entries. */
+int lig_read_class(lig_ctx* ctx, uint64_t epoch, int critical, int adapter_id, int* status,
+                   int* n_survivors, uint16_t* list);
+
+/* ---- introspection ------------------------------------------------------------------------- */
+const char* lig_last_error(void);            /* thread-local, never NULL */
+const char* lig_version(void);
+int         lig_abi_version(void);
+int         lig_device_count(void);          /* 0 when no CUDA device / driver */
+uint64_t    lig_kernel_launches(const lig_ctx* ctx);  /* kernels this ctx launched so far */
+int         lig_sm_count(const lig_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LIG_H_ */

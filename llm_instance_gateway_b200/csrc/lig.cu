@@ -1,0 +1,581 @@
+// lig.cu — the C ABI of include/lig.h over the sm_100a kernels of lig_device.cuh.
+//
+// Host-side responsibilities only: context and HBM/pinned allocation, snapshot slots (two resident
+// epochs), stream/event ordering, the chunk-pipelined host-buffer path, error reporting.  There is
+// deliberately no CPU implementation of the scheduling path in this library: if CUDA is missing
+// every entry point fails with LIG_ERR_CUDA.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "lig_device.cuh"
+
+using namespace lig;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                      \
+  do {                                                                                      \
+    cudaError_t e__ = (expr);                                                               \
+    if (e__ != cudaSuccess)                                                                 \
+      return fail(LIG_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__),    \
+                  __FILE__, __LINE__);                                                      \
+  } while (0)
+
+inline int words_for(int P) { return (P + 31) / 32; }
+
+struct Layout {  // offsets into the packed blob
+  size_t kv, q, na, ma, bitmap, total;
+};
+
+Layout layout_for(int P, int A) {
+  const size_t Ppad = (size_t)words_for(P) * 32;
+  Layout l;
+  l.kv = 0;
+  l.q = l.kv + Ppad * sizeof(double);
+  l.na = l.q + Ppad * sizeof(int32_t);
+  l.ma = l.na + Ppad * sizeof(uint16_t);
+  l.bitmap = l.ma + Ppad * sizeof(uint16_t);
+  l.total = l.bitmap + (size_t)A * words_for(P) * sizeof(uint32_t);
+  l.total = (l.total + 15) & ~(size_t)15;
+  if (l.total == 0) l.total = 16;
+  return l;
+}
+
+struct Slot {
+  bool valid = false;
+  uint64_t epoch = 0;
+  int P = 0, A = 0, W = 0;
+  unsigned char* d_blob = nullptr;
+  ClassEntry* d_cls = nullptr;
+  uint16_t* d_lists = nullptr;
+  unsigned char* h_blob = nullptr;  // pinned staging for host uploads
+  cudaEvent_t ready = nullptr;      // class tables built
+  cudaEvent_t idle = nullptr;       // last batch that read this slot
+  uint64_t stamp = 0;               // upload order, to pick the slot to overwrite
+};
+
+constexpr int kPipeStreams = 3;
+constexpr int kChunk = 1 << 16;  // requests per chunk of the host-buffer pipeline (1 MiB in)
+
+}  // namespace
+
+struct lig_ctx {
+  int device = 0;
+  int max_pods = 0, max_adapters = 0, max_batch = 0;
+  int sm_count = 0;
+  size_t smem_optin = 0;
+  lig_thresholds thr{0.8, 5, 50};
+  Slot slot[2];
+  uint64_t stamp = 0;
+  cudaStream_t s_up = nullptr;               // snapshot uploads + table builds
+  cudaStream_t s_pipe[kPipeStreams] = {};    // host-buffer batches
+  lig_req* d_reqs = nullptr;                 // device staging for host-buffer batches
+  lig_pick* d_out = nullptr;
+  uint32_t* d_masks = nullptr;               // scan test hook staging (lazily sized)
+  size_t d_masks_bytes = 0;
+  lig_req* h_reqs = nullptr;                 // pinned bounce buffers for pageable callers
+  lig_pick* h_out = nullptr;
+  std::atomic<uint64_t> launches{0};
+  std::mutex mu;
+};
+
+namespace {
+
+SnapView view_of(const Slot& s) {
+  const Layout l = layout_for(s.P, s.A);
+  SnapView v;
+  v.kv = reinterpret_cast<const double*>(s.d_blob + l.kv);
+  v.q = reinterpret_cast<const int*>(s.d_blob + l.q);
+  v.n_active = reinterpret_cast<const uint16_t*>(s.d_blob + l.na);
+  v.max_active = reinterpret_cast<const uint16_t*>(s.d_blob + l.ma);
+  v.bitmap = reinterpret_cast<const uint32_t*>(s.d_blob + l.bitmap);
+  v.P = s.P;
+  v.A = s.A;
+  v.W = s.W;
+  return v;
+}
+
+Thr thr_of(const lig_ctx* c) {
+  return Thr{c->thr.kv_cache_threshold, (long long)c->thr.queue_threshold_critical,
+             (long long)c->thr.queueing_threshold_lora};
+}
+
+Slot* find_slot(lig_ctx* c, uint64_t epoch) {
+  for (auto& s : c->slot)
+    if (s.valid && s.epoch == epoch) return &s;
+  return nullptr;
+}
+
+int resolve_slot(lig_ctx* c, uint64_t epoch, Slot** out) {
+  if (!c->slot[0].valid && !c->slot[1].valid)
+    return fail(LIG_ERR_NO_SNAPSHOT, "no snapshot uploaded yet");
+  Slot* s = find_slot(c, epoch);
+  if (!s)
+    return fail(LIG_ERR_STALE_EPOCH, "epoch %llu is not resident (resident: %llu%s, %llu%s)",
+                (unsigned long long)epoch, (unsigned long long)c->slot[0].epoch,
+                c->slot[0].valid ? "" : " [empty]", (unsigned long long)c->slot[1].epoch,
+                c->slot[1].valid ? "" : " [empty]");
+  *out = s;
+  return 0;
+}
+
+// Does the tree-walking kernel stage the pod columns in shared memory for this W?
+bool staged_fits(const lig_ctx* c, int W) {
+  return scratch_bytes(W) + staged_bytes(W) <= c->smem_optin;
+}
+
+// Enqueue the class-table build for slot s on `stream`.
+int launch_class_build(lig_ctx* c, Slot& s, cudaStream_t stream) {
+  const SnapView v = view_of(s);
+  const int n_classes = 2 * (s.A + 1);
+  const int ctas_needed = (n_classes + kWarpsPerCta - 1) / kWarpsPerCta;
+  const bool staged = s.P > 0 && staged_fits(c, s.W);
+  const size_t smem = scratch_bytes(s.W > 0 ? s.W : 1) + (staged ? staged_bytes(s.W) : 0);
+  const int ctas_per_sm = staged ? (smem > 110 * 1024 ? 1 : 2) : 4;
+  int grid = ctas_needed < c->sm_count * ctas_per_sm ? ctas_needed : c->sm_count * ctas_per_sm;
+  if (grid < 1) grid = 1;
+  if (staged) {
+    lig_class_build_kernel<true><<<grid, kCtaThreads, smem, stream>>>(v, thr_of(c), s.d_cls,
+                                                                       s.d_lists, s.P > 0 ? s.P : 1);
+  } else {
+    lig_class_build_kernel<false><<<grid, kCtaThreads, smem, stream>>>(v, thr_of(c), s.d_cls,
+                                                                        s.d_lists, s.P > 0 ? s.P : 1);
+  }
+  CUDA_TRY(cudaGetLastError());
+  c->launches++;
+  return 0;
+}
+
+int launch_pick(lig_ctx* c, const Slot& s, uint64_t seed, const lig_req* d_reqs, int R,
+                lig_pick* d_out, cudaStream_t stream) {
+  if (R == 0) return 0;
+  const int per_cta = kPickThreads * kPickPerThread;
+  const int grid = (R + per_cta - 1) / per_cta;
+  lig_pick_stream_kernel<<<grid, kPickThreads, 0, stream>>>(
+      reinterpret_cast<const int4*>(d_reqs), reinterpret_cast<int2*>(d_out), R,
+      reinterpret_cast<const uint2*>(s.d_cls), s.d_lists, s.P > 0 ? s.P : 1, s.A, seed);
+  CUDA_TRY(cudaGetLastError());
+  c->launches++;
+  return 0;
+}
+
+int launch_scan(lig_ctx* c, const Slot& s, uint64_t seed, const lig_req* d_reqs, int R,
+                lig_pick* d_out, uint32_t* d_masks, cudaStream_t stream) {
+  if (R == 0) return 0;
+  const SnapView v = view_of(s);
+  const bool staged = s.P > 0 && staged_fits(c, s.W);
+  const size_t smem = scratch_bytes(s.W > 0 ? s.W : 1) + (staged ? staged_bytes(s.W) : 0);
+  const int ctas_per_sm = staged ? (smem > 110 * 1024 ? 1 : 2) : 4;
+  const int ctas_needed = (R + kWarpsPerCta - 1) / kWarpsPerCta;
+  int grid = ctas_needed < c->sm_count * ctas_per_sm ? ctas_needed : c->sm_count * ctas_per_sm;
+  if (staged) {
+    lig_scan_kernel<true><<<grid, kCtaThreads, smem, stream>>>(
+        v, thr_of(c), reinterpret_cast<const int4*>(d_reqs), reinterpret_cast<int2*>(d_out), R,
+        d_masks, seed);
+  } else {
+    lig_scan_kernel<false><<<grid, kCtaThreads, smem, stream>>>(
+        v, thr_of(c), reinterpret_cast<const int4*>(d_reqs), reinterpret_cast<int2*>(d_out), R,
+        d_masks, seed);
+  }
+  CUDA_TRY(cudaGetLastError());
+  c->launches++;
+  return 0;
+}
+
+// Pick the slot a new epoch overwrites: the one already holding that epoch, else an empty one,
+// else the older of the two.
+Slot& victim_slot(lig_ctx* c, uint64_t epoch) {
+  if (Slot* s = find_slot(c, epoch)) return *s;
+  if (!c->slot[0].valid) return c->slot[0];
+  if (!c->slot[1].valid) return c->slot[1];
+  return c->slot[0].stamp <= c->slot[1].stamp ? c->slot[0] : c->slot[1];
+}
+
+int check_shape(const lig_ctx* c, int P, int A) {
+  if (P < 0 || P > c->max_pods)
+    return fail(LIG_ERR_INVALID, "P=%d outside [0, max_pods=%d]", P, c->max_pods);
+  if (A < 0 || A > c->max_adapters)
+    return fail(LIG_ERR_INVALID, "A=%d outside [0, max_adapters=%d]", A, c->max_adapters);
+  return 0;
+}
+
+bool is_dma_able_host(const void* p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* lig_last_error(void) { return g_err; }
+const char* lig_version(void) { return "lig-b200 0.1 (sm_100a)"; }
+int lig_abi_version(void) { return LIG_ABI_VERSION; }
+
+int lig_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+size_t lig_snapshot_bytes(int P, int A) {
+  if (P < 0 || A < 0) return 0;
+  return layout_for(P, A).total;
+}
+
+int lig_pack_pods(int P, const int64_t* q, const int64_t* na, const int64_t* ma, int32_t* q_out,
+                  uint16_t* na_out, uint16_t* ma_out) {
+  if (P < 0 || (P > 0 && (!q || !na || !ma || !q_out || !na_out || !ma_out)))
+    return fail(LIG_ERR_INVALID, "lig_pack_pods: null array");
+  for (int i = 0; i < P; ++i) {
+    if (q[i] < INT32_MIN || q[i] > INT32_MAX)
+      return fail(LIG_ERR_RANGE, "pod %d: WaitingQueueSize %lld does not fit int32", i,
+                  (long long)q[i]);
+    if (na[i] < 0 || na[i] > LIG_MAX_ADAPTERS)
+      return fail(LIG_ERR_RANGE, "pod %d: len(ActiveModels) %lld outside [0, %d]", i,
+                  (long long)na[i], LIG_MAX_ADAPTERS);
+    q_out[i] = (int32_t)q[i];
+    na_out[i] = (uint16_t)na[i];
+    ma_out[i] = (uint16_t)(ma[i] < 0 ? 0 : (ma[i] > 65535 ? 65535 : ma[i]));
+  }
+  return 0;
+}
+
+int lig_pack_snapshot(void* blob, int P, int A, const double* kv, const int32_t* q,
+                      const uint16_t* na, const uint16_t* ma, const uint32_t* bitmap) {
+  if (!blob || P < 0 || A < 0) return fail(LIG_ERR_INVALID, "lig_pack_snapshot: bad argument");
+  if (P > 0 && (!kv || !q || !na || !ma)) return fail(LIG_ERR_INVALID, "null pod column");
+  if (A > 0 && P > 0 && !bitmap) return fail(LIG_ERR_INVALID, "null bitmap");
+  const Layout l = layout_for(P, A);
+  unsigned char* b = static_cast<unsigned char*>(blob);
+  memset(b, 0, l.total);
+  if (P > 0) {
+    memcpy(b + l.kv, kv, (size_t)P * sizeof(double));
+    memcpy(b + l.q, q, (size_t)P * sizeof(int32_t));
+    memcpy(b + l.na, na, (size_t)P * sizeof(uint16_t));
+    memcpy(b + l.ma, ma, (size_t)P * sizeof(uint16_t));
+    if (A > 0) memcpy(b + l.bitmap, bitmap, (size_t)A * words_for(P) * sizeof(uint32_t));
+    // bits of padding pods must be clear in the last word of every row
+    const int W = words_for(P), rem = P & 31;
+    if (rem) {
+      uint32_t* bm = reinterpret_cast<uint32_t*>(b + l.bitmap);
+      const uint32_t keep = (1u << rem) - 1u;
+      for (int a = 0; a < A; ++a) bm[(size_t)a * W + (W - 1)] &= keep;
+    }
+  }
+  return 0;
+}
+
+static int create_impl(lig_ctx* c, int device, int max_pods, int max_adapters, int max_batch) {
+  CUDA_TRY(cudaSetDevice(device));
+  c->device = device;
+  c->max_pods = max_pods;
+  c->max_adapters = max_adapters;
+  c->max_batch = max_batch;
+  int v = 0;
+  CUDA_TRY(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device));
+  c->sm_count = v;
+  CUDA_TRY(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+  c->smem_optin = (size_t)v;
+  CUDA_TRY(cudaFuncSetAttribute(lig_class_build_kernel<true>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, v));
+  CUDA_TRY(cudaFuncSetAttribute(lig_class_build_kernel<false>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, v));
+  CUDA_TRY(cudaFuncSetAttribute(lig_scan_kernel<true>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, v));
+  CUDA_TRY(cudaFuncSetAttribute(lig_scan_kernel<false>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, v));
+  if (scratch_bytes(words_for(max_pods)) > c->smem_optin)
+    return fail(LIG_ERR_INVALID, "max_pods=%d needs %zu B of per-CTA scratch, device allows %zu",
+                max_pods, scratch_bytes(words_for(max_pods)), c->smem_optin);
+  const Layout l = layout_for(max_pods, max_adapters);
+  const size_t n_classes = 2 * ((size_t)max_adapters + 1);
+  for (auto& s : c->slot) {
+    CUDA_TRY(cudaMalloc(&s.d_blob, l.total));
+    CUDA_TRY(cudaMalloc(&s.d_cls, n_classes * sizeof(ClassEntry)));
+    CUDA_TRY(cudaMalloc(&s.d_lists, n_classes * (size_t)max_pods * sizeof(uint16_t)));
+    CUDA_TRY(cudaHostAlloc(&s.h_blob, l.total, cudaHostAllocDefault));
+    CUDA_TRY(cudaEventCreateWithFlags(&s.ready, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&s.idle, cudaEventDisableTiming));
+  }
+  CUDA_TRY(cudaStreamCreateWithFlags(&c->s_up, cudaStreamNonBlocking));
+  for (auto& s : c->s_pipe) CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  CUDA_TRY(cudaMalloc(&c->d_reqs, (size_t)max_batch * sizeof(lig_req)));
+  CUDA_TRY(cudaMalloc(&c->d_out, (size_t)max_batch * sizeof(lig_pick)));
+  CUDA_TRY(cudaHostAlloc(&c->h_reqs, (size_t)max_batch * sizeof(lig_req), cudaHostAllocDefault));
+  CUDA_TRY(cudaHostAlloc(&c->h_out, (size_t)max_batch * sizeof(lig_pick), cudaHostAllocDefault));
+  return 0;
+}
+
+int lig_create(lig_ctx** out, int device, int max_pods, int max_adapters, int max_batch) {
+  if (!out) return fail(LIG_ERR_INVALID, "lig_create: out is null");
+  *out = nullptr;
+  if (max_pods < 1 || max_pods > LIG_MAX_PODS)
+    return fail(LIG_ERR_INVALID, "max_pods=%d outside [1, %d]", max_pods, LIG_MAX_PODS);
+  if (max_adapters < 0 || max_adapters > LIG_MAX_ADAPTERS)
+    return fail(LIG_ERR_INVALID, "max_adapters=%d outside [0, %d]", max_adapters, LIG_MAX_ADAPTERS);
+  if (max_batch < 1) return fail(LIG_ERR_INVALID, "max_batch=%d must be >= 1", max_batch);
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(LIG_ERR_CUDA, "no CUDA device available (%s); this library has no CPU path",
+                e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  }
+  if (device < 0 || device >= ndev)
+    return fail(LIG_ERR_INVALID, "device %d outside [0, %d)", device, ndev);
+  lig_ctx* c = new lig_ctx();
+  if (int rc = create_impl(c, device, max_pods, max_adapters, max_batch)) {
+    char keep[sizeof(g_err)];
+    memcpy(keep, g_err, sizeof(keep));
+    lig_destroy(c);
+    memcpy(g_err, keep, sizeof(keep));
+    return rc;
+  }
+  *out = c;
+  return 0;
+}
+
+void lig_destroy(lig_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  for (auto& s : c->slot) {
+    cudaFree(s.d_blob);
+    cudaFree(s.d_cls);
+    cudaFree(s.d_lists);
+    cudaFreeHost(s.h_blob);
+    if (s.ready) cudaEventDestroy(s.ready);
+    if (s.idle) cudaEventDestroy(s.idle);
+  }
+  if (c->s_up) cudaStreamDestroy(c->s_up);
+  for (auto& s : c->s_pipe)
+    if (s) cudaStreamDestroy(s);
+  cudaFree(c->d_reqs);
+  cudaFree(c->d_out);
+  cudaFree(c->d_masks);
+  cudaFreeHost(c->h_reqs);
+  cudaFreeHost(c->h_out);
+  delete c;
+}
+
+int lig_set_thresholds(lig_ctx* c, const lig_thresholds* t) {
+  if (!c || !t) return fail(LIG_ERR_INVALID, "lig_set_thresholds: null argument");
+  std::lock_guard<std::mutex> lk(c->mu);
+  c->thr = *t;
+  // resident class tables were built with the old thresholds: rebuild them
+  CUDA_TRY(cudaSetDevice(c->device));
+  for (auto& s : c->slot) {
+    if (!s.valid) continue;
+    CUDA_TRY(cudaStreamWaitEvent(c->s_up, s.idle, 0));
+    if (int rc = launch_class_build(c, s, c->s_up)) return rc;
+    CUDA_TRY(cudaEventRecord(s.ready, c->s_up));
+  }
+  CUDA_TRY(cudaStreamSynchronize(c->s_up));
+  return 0;
+}
+
+int lig_get_thresholds(const lig_ctx* c, lig_thresholds* t) {
+  if (!c || !t) return fail(LIG_ERR_INVALID, "lig_get_thresholds: null argument");
+  *t = c->thr;
+  return 0;
+}
+
+int lig_upload_snapshot(lig_ctx* c, uint64_t epoch, int P, int A, const double* kv,
+                        const int32_t* q, const uint16_t* na, const uint16_t* ma,
+                        const uint32_t* bitmap) {
+  if (!c) return fail(LIG_ERR_INVALID, "lig_upload_snapshot: ctx is null");
+  if (int rc = check_shape(c, P, A)) return rc;
+  std::lock_guard<std::mutex> lk(c->mu);
+  CUDA_TRY(cudaSetDevice(c->device));
+  Slot& s = victim_slot(c, epoch);
+  // the pinned staging blob of this slot may still be in flight from its previous upload
+  CUDA_TRY(cudaStreamSynchronize(c->s_up));
+  if (int rc = lig_pack_snapshot(s.h_blob, P, A, kv, q, na, ma, bitmap)) return rc;
+  CUDA_TRY(cudaStreamWaitEvent(c->s_up, s.idle, 0));  // batches still reading the old content
+  s.valid = false;
+  CUDA_TRY(cudaMemcpyAsync(s.d_blob, s.h_blob, layout_for(P, A).total, cudaMemcpyHostToDevice,
+                           c->s_up));
+  s.P = P;
+  s.A = A;
+  s.W = words_for(P);
+  if (int rc = launch_class_build(c, s, c->s_up)) return rc;
+  CUDA_TRY(cudaEventRecord(s.ready, c->s_up));
+  CUDA_TRY(cudaStreamSynchronize(c->s_up));
+  s.epoch = epoch;
+  s.stamp = ++c->stamp;
+  s.valid = true;
+  return 0;
+}
+
+int lig_upload_snapshot_device(lig_ctx* c, uint64_t epoch, int P, int A, const void* d_blob,
+                               void* stream) {
+  if (!c || !d_blob) return fail(LIG_ERR_INVALID, "lig_upload_snapshot_device: null argument");
+  if (int rc = check_shape(c, P, A)) return rc;
+  std::lock_guard<std::mutex> lk(c->mu);
+  CUDA_TRY(cudaSetDevice(c->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Slot& s = victim_slot(c, epoch);
+  CUDA_TRY(cudaStreamWaitEvent(st, s.idle, 0));
+  CUDA_TRY(cudaStreamWaitEvent(st, s.ready, 0));
+  CUDA_TRY(cudaMemcpyAsync(s.d_blob, d_blob, layout_for(P, A).total, cudaMemcpyDeviceToDevice, st));
+  s.P = P;
+  s.A = A;
+  s.W = words_for(P);
+  if (int rc = launch_class_build(c, s, st)) return rc;
+  CUDA_TRY(cudaEventRecord(s.ready, st));
+  s.epoch = epoch;
+  s.stamp = ++c->stamp;
+  s.valid = true;
+  return 0;
+}
+
+int lig_schedule_batch_device(lig_ctx* c, uint64_t epoch, uint64_t seed, const lig_req* d_reqs,
+                              int R, lig_pick* d_out, void* stream) {
+  if (!c || R < 0 || (R > 0 && (!d_reqs || !d_out)))
+    return fail(LIG_ERR_INVALID, "lig_schedule_batch_device: bad argument");
+  std::lock_guard<std::mutex> lk(c->mu);
+  Slot* s = nullptr;
+  if (int rc = resolve_slot(c, epoch, &s)) return rc;
+  CUDA_TRY(cudaSetDevice(c->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUDA_TRY(cudaStreamWaitEvent(st, s->ready, 0));
+  if (int rc = launch_pick(c, *s, seed, d_reqs, R, d_out, st)) return rc;
+  CUDA_TRY(cudaEventRecord(s->idle, st));
+  return 0;
+}
+
+int lig_schedule_scan_device(lig_ctx* c, uint64_t epoch, uint64_t seed, const lig_req* d_reqs,
+                             int R, lig_pick* d_out, uint32_t* d_masks, void* stream) {
+  if (!c || R < 0 || (R > 0 && (!d_reqs || !d_out)))
+    return fail(LIG_ERR_INVALID, "lig_schedule_scan_device: bad argument");
+  std::lock_guard<std::mutex> lk(c->mu);
+  Slot* s = nullptr;
+  if (int rc = resolve_slot(c, epoch, &s)) return rc;
+  CUDA_TRY(cudaSetDevice(c->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUDA_TRY(cudaStreamWaitEvent(st, s->ready, 0));
+  if (int rc = launch_scan(c, *s, seed, d_reqs, R, d_out, d_masks, st)) return rc;
+  CUDA_TRY(cudaEventRecord(s->idle, st));
+  return 0;
+}
+
+int lig_schedule_batch(lig_ctx* c, uint64_t epoch, uint64_t seed, const lig_req* reqs, int R,
+                       lig_pick* out) {
+  if (!c || R < 0 || (R > 0 && (!reqs || !out)))
+    return fail(LIG_ERR_INVALID, "lig_schedule_batch: bad argument");
+  if (R > c->max_batch)
+    return fail(LIG_ERR_INVALID, "R=%d exceeds max_batch=%d", R, c->max_batch);
+  std::lock_guard<std::mutex> lk(c->mu);
+  Slot* s = nullptr;
+  if (int rc = resolve_slot(c, epoch, &s)) return rc;
+  if (R == 0) return 0;
+  CUDA_TRY(cudaSetDevice(c->device));
+  // Pinned (or managed) caller buffers are DMA'd directly; pageable ones bounce through the
+  // ctx's pinned buffers chunk by chunk, so the CPU copy of chunk i+1 overlaps the DMA of chunk i.
+  const bool in_pinned = is_dma_able_host(reqs);
+  const bool out_pinned = is_dma_able_host(out);
+  const int n_chunks = (R + kChunk - 1) / kChunk;
+  for (int k = 0; k < n_chunks; ++k) {
+    const int lo = k * kChunk;
+    const int n = (R - lo) < kChunk ? (R - lo) : kChunk;
+    cudaStream_t st = c->s_pipe[k % kPipeStreams];
+    if (k < kPipeStreams) CUDA_TRY(cudaStreamWaitEvent(st, s->ready, 0));
+    const lig_req* src = reqs + lo;
+    if (!in_pinned) {
+      memcpy(c->h_reqs + lo, reqs + lo, (size_t)n * sizeof(lig_req));
+      src = c->h_reqs + lo;
+    }
+    CUDA_TRY(cudaMemcpyAsync(c->d_reqs + lo, src, (size_t)n * sizeof(lig_req),
+                             cudaMemcpyHostToDevice, st));
+    if (int rc = launch_pick(c, *s, seed, c->d_reqs + lo, n, c->d_out + lo, st)) return rc;
+    CUDA_TRY(cudaMemcpyAsync(out_pinned ? out + lo : c->h_out + lo, c->d_out + lo,
+                             (size_t)n * sizeof(lig_pick), cudaMemcpyDeviceToHost, st));
+  }
+  for (int k = 0; k < kPipeStreams && k < n_chunks; ++k) {
+    CUDA_TRY(cudaEventRecord(s->idle, c->s_pipe[k]));  // last record wins; all are synced below
+    CUDA_TRY(cudaStreamSynchronize(c->s_pipe[k]));
+  }
+  if (!out_pinned) memcpy(out, c->h_out, (size_t)R * sizeof(lig_pick));
+  return 0;
+}
+
+int lig_schedule_scan(lig_ctx* c, uint64_t epoch, uint64_t seed, const lig_req* reqs, int R,
+                      lig_pick* out, uint32_t* masks) {
+  if (!c || R < 0 || (R > 0 && (!reqs || !out)))
+    return fail(LIG_ERR_INVALID, "lig_schedule_scan: bad argument");
+  if (R > c->max_batch)
+    return fail(LIG_ERR_INVALID, "R=%d exceeds max_batch=%d", R, c->max_batch);
+  std::lock_guard<std::mutex> lk(c->mu);
+  Slot* s = nullptr;
+  if (int rc = resolve_slot(c, epoch, &s)) return rc;
+  if (R == 0) return 0;
+  CUDA_TRY(cudaSetDevice(c->device));
+  cudaStream_t st = c->s_pipe[0];
+  const size_t mask_bytes = masks ? (size_t)R * (s->W > 0 ? s->W : 1) * sizeof(uint32_t) : 0;
+  if (mask_bytes > c->d_masks_bytes) {
+    CUDA_TRY(cudaStreamSynchronize(st));
+    cudaFree(c->d_masks);
+    c->d_masks = nullptr;
+    c->d_masks_bytes = 0;
+    CUDA_TRY(cudaMalloc(&c->d_masks, mask_bytes));
+    c->d_masks_bytes = mask_bytes;
+  }
+  CUDA_TRY(cudaStreamWaitEvent(st, s->ready, 0));
+  CUDA_TRY(cudaMemcpyAsync(c->d_reqs, reqs, (size_t)R * sizeof(lig_req), cudaMemcpyHostToDevice, st));
+  if (int rc = launch_scan(c, *s, seed, c->d_reqs, R, c->d_out, masks ? c->d_masks : nullptr, st))
+    return rc;
+  CUDA_TRY(cudaMemcpyAsync(out, c->d_out, (size_t)R * sizeof(lig_pick), cudaMemcpyDeviceToHost, st));
+  if (masks && s->W > 0)
+    CUDA_TRY(cudaMemcpyAsync(masks, c->d_masks, mask_bytes, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaEventRecord(s->idle, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int lig_read_class(lig_ctx* c, uint64_t epoch, int critical, int adapter_id, int* status,
+                   int* n_survivors, uint16_t* list) {
+  if (!c || !status || !n_survivors) return fail(LIG_ERR_INVALID, "lig_read_class: null argument");
+  std::lock_guard<std::mutex> lk(c->mu);
+  Slot* s = nullptr;
+  if (int rc = resolve_slot(c, epoch, &s)) return rc;
+  CUDA_TRY(cudaSetDevice(c->device));
+  CUDA_TRY(cudaEventSynchronize(s->ready));
+  const int a = (adapter_id >= 0 && adapter_id < s->A) ? adapter_id : s->A;
+  const int cls = (critical ? 1 : 0) * (s->A + 1) + a;
+  ClassEntry e;
+  CUDA_TRY(cudaMemcpy(&e, s->d_cls + cls, sizeof(e), cudaMemcpyDeviceToHost));
+  *n_survivors = (int)(e.n_status & 0xffffu);
+  *status = (int)(e.n_status >> 16);
+  if (list && *n_survivors > 0)
+    CUDA_TRY(cudaMemcpy(list, s->d_lists + (size_t)cls * (s->P > 0 ? s->P : 1),
+                        (size_t)*n_survivors * sizeof(uint16_t), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+uint64_t lig_kernel_launches(const lig_ctx* c) { return c ? c->launches.load() : 0; }
+int lig_sm_count(const lig_ctx* c) { return c ? c->sm_count : 0; }
+
+}  // extern "C"

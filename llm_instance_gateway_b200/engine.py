@@ -1,0 +1,101 @@
+"""Thin object wrapper over the C ABI (one ``lig_ctx`` = one CUDA device)."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import numpy as np
+
+from . import _native as N
+from .packer import PICK_DTYPE, REQ_DTYPE, PackedSnapshot, _ptr
+
+
+class Engine:
+    def __init__(self, device: int = 0, max_pods: int = 4096, max_adapters: int = 1024,
+                 max_batch: int = 1 << 20):
+        self._lib = N.load()
+        self._ctx = C.c_void_p()
+        N.check(self._lib.lig_create(C.byref(self._ctx), device, max_pods, max_adapters, max_batch))
+        self.device = device
+        self.max_batch = max_batch
+
+    def close(self) -> None:
+        if getattr(self, "_ctx", None):
+            self._lib.lig_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # ---- thresholds (scheduler.go:15-24) ----
+    def set_thresholds(self, kv_cache_threshold=0.8, queue_threshold_critical=5,
+                       queueing_threshold_lora=50) -> None:
+        t = N.LigThresholds(kv_cache_threshold, queue_threshold_critical, queueing_threshold_lora)
+        N.check(self._lib.lig_set_thresholds(self._ctx, C.byref(t)))
+
+    # ---- snapshots ----
+    def upload_snapshot(self, epoch: int, snap: PackedSnapshot) -> None:
+        N.check(self._lib.lig_upload_snapshot(self._ctx, epoch, snap.P, snap.A, _ptr(snap.kv),
+                                              _ptr(snap.q), _ptr(snap.n_active),
+                                              _ptr(snap.max_active), _ptr(snap.bitmap)))
+
+    def upload_snapshot_device(self, epoch: int, P: int, A: int, d_blob: int, stream: int = 0) -> None:
+        N.check(self._lib.lig_upload_snapshot_device(self._ctx, epoch, P, A, d_blob, stream or None))
+
+    # ---- host-buffer hot path ----
+    def schedule_batch(self, epoch: int, seed: int, reqs: np.ndarray,
+                       out: Optional[np.ndarray] = None) -> np.ndarray:
+        assert reqs.dtype == REQ_DTYPE and reqs.flags.c_contiguous
+        R = int(reqs.shape[0])
+        if out is None:
+            out = np.empty(R, dtype=PICK_DTYPE)
+        N.check(self._lib.lig_schedule_batch(self._ctx, epoch, seed, _ptr(reqs), R, _ptr(out)))
+        return out
+
+    def schedule_batch_ptr(self, epoch: int, seed: int, h_reqs: int, R: int, h_out: int) -> None:
+        N.check(self._lib.lig_schedule_batch(self._ctx, epoch, seed, h_reqs, R, h_out))
+
+    def schedule_scan(self, epoch: int, seed: int, reqs: np.ndarray, want_masks: bool = True,
+                      W: int = 0) -> Tuple[np.ndarray, Optional[np.ndarray]]:
+        assert reqs.dtype == REQ_DTYPE and reqs.flags.c_contiguous
+        R = int(reqs.shape[0])
+        out = np.empty(R, dtype=PICK_DTYPE)
+        masks = np.zeros((R, W), dtype=np.uint32) if want_masks else None
+        N.check(self._lib.lig_schedule_scan(self._ctx, epoch, seed, _ptr(reqs), R, _ptr(out),
+                                            _ptr(masks) if masks is not None else None))
+        return out, masks
+
+    # ---- HBM-resident hot path (device pointers, async on `stream`) ----
+    def schedule_batch_device(self, epoch: int, seed: int, d_reqs: int, R: int, d_out: int,
+                              stream: int = 0) -> None:
+        N.check(self._lib.lig_schedule_batch_device(self._ctx, epoch, seed, d_reqs, R, d_out,
+                                                    stream or None))
+
+    def schedule_scan_device(self, epoch: int, seed: int, d_reqs: int, R: int, d_out: int,
+                             d_masks: int = 0, stream: int = 0) -> None:
+        N.check(self._lib.lig_schedule_scan_device(self._ctx, epoch, seed, d_reqs, R, d_out,
+                                                   d_masks or None, stream or None))
+
+    def read_class(self, epoch: int, critical: bool, adapter_id: int, P: int):
+        status, n = C.c_int(), C.c_int()
+        lst = np.zeros(max(P, 1), dtype=np.uint16)
+        N.check(self._lib.lig_read_class(self._ctx, epoch, int(bool(critical)), adapter_id,
+                                         C.byref(status), C.byref(n), _ptr(lst)))
+        return status.value, n.value, lst[: n.value].copy()
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(self._lib.lig_kernel_launches(self._ctx))
+
+    @property
+    def sm_count(self) -> int:
+        return int(self._lib.lig_sm_count(self._ctx))

@@ -1,0 +1,112 @@
+"""Seeded synthetic snapshots and request batches (the distributions of SURVEY.md section 8d).
+
+Shared by bench.py and the parity tests so both see identical inputs.  Pure numpy, no GPU.
+Adapter a is named ``adapter-<a>`` (the naming of the reference's load generator,
+pkg/ext-proc/test/benchmark/benchmark.go:108-110); pods are ``pod-<i>`` / ``address-<i>``
+(pkg/ext-proc/test/utils.go:73-80).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List
+
+import numpy as np
+
+from .packer import REQ_DTYPE, PackedSnapshot, pack_columns
+from .backend import Pod
+
+SNAPSHOT_SEED = 0xC0FFEE
+REQUEST_SEED = 0xBADC0DE
+UNKNOWN_MODEL = "base-model"     # a ResolvedTargetModel that is in no pod's ActiveModels
+
+# BASELINE.json configs (R, P, A)
+CONFIGS = {
+    "C1": dict(R=5000, P=8, A=4),
+    "C2": dict(R=1024, P=64, A=32),
+    "C3": dict(R=65536, P=512, A=256),
+    "C4": dict(R=1 << 20, P=4096, A=1024),
+    "C5": dict(R=100_000, P=256, A=64),
+}
+
+
+def adapter_name(a: int) -> str:
+    return f"adapter-{a}"
+
+
+def _zipf_weights(A: int, s: float = 1.1) -> np.ndarray:
+    w = 1.0 / np.power(np.arange(1, A + 1, dtype=np.float64), s)
+    return w / w.sum()
+
+
+@dataclass
+class SyntheticSnapshot:
+    packed: PackedSnapshot
+    active: List[List[int]]      # per pod: adapter ids in ActiveModels
+    max_active64: np.ndarray     # the un-saturated Go-width value
+    q64: np.ndarray
+
+    def oracle_pods(self) -> List[dict]:
+        p = self.packed
+        return [dict(name=f"pod-{i}", address=f"address-{i}",
+                     waiting_queue_size=int(self.q64[i]),
+                     kv_cache_usage_percent=float(p.kv[i]),
+                     max_active_models=int(self.max_active64[i]),
+                     active_models=[adapter_name(a) for a in self.active[i]])
+                for i in range(p.P)]
+
+    def adapter_names(self) -> List[str]:
+        return [adapter_name(a) for a in range(self.packed.A)]
+
+
+def make_snapshot(P: int, A: int, seed: int = SNAPSHOT_SEED) -> SyntheticSnapshot:
+    rng = np.random.default_rng(seed)
+    # WaitingQueueSize: 70 % U{0..8}, 25 % U{9..60}, 5 % U{61..200}
+    u = rng.random(P)
+    q = np.where(u < 0.70, rng.integers(0, 9, P),
+                 np.where(u < 0.95, rng.integers(9, 61, P), rng.integers(61, 201, P))).astype(np.int64)
+    # KVCacheUsagePercent: U[0,1); half the pods rounded to a 1e-3 grid (exact ties)
+    kv = rng.random(P)
+    grid = rng.random(P) < 0.5
+    kv = np.where(grid, np.round(kv * 1000.0) / 1000.0, kv)
+    # MaxActiveModels in {0 (2 %), 4, 8, 16}
+    ma = rng.choice(np.array([4, 8, 16]), size=P).astype(np.int64)
+    ma[rng.random(P) < 0.02] = 0
+    W = (P + 31) // 32
+    bitmap = np.zeros((A, W), dtype=np.uint32)
+    w = _zipf_weights(A) if A > 0 else None
+    active: List[List[int]] = []
+    na = np.zeros(P, dtype=np.int64)
+    for p in range(P):
+        size = int(rng.integers(0, ma[p] + 2))          # 0 .. MaxActive+1 (over-full allowed)
+        size = min(size, A)
+        ids = sorted(rng.choice(A, size=size, replace=False, p=w).tolist()) if size else []
+        active.append(ids)
+        na[p] = len(ids)
+        for a in ids:
+            bitmap[a, p >> 5] |= np.uint32(1 << (p & 31))
+    ids_map = {adapter_name(a): a for a in range(A)}
+    packed = pack_columns(kv, q, na, ma, bitmap, ids_map,
+                          [Pod(f"pod-{i}", f"address-{i}") for i in range(P)])
+    return SyntheticSnapshot(packed=packed, active=active, max_active64=ma, q64=q)
+
+
+def make_requests(R: int, A: int, seed: int = REQUEST_SEED, out: np.ndarray = None) -> np.ndarray:
+    """adapter ~ Zipf(1.1) over A with 3 % unknown (id = A); critical ~ Bernoulli(0.5)."""
+    rng = np.random.default_rng(seed)
+    reqs = out if out is not None else np.zeros(R, dtype=REQ_DTYPE)
+    if A > 0:
+        cdf = np.cumsum(_zipf_weights(A))
+        ids = np.searchsorted(cdf, rng.random(R), side="right").astype(np.int32)
+        ids = np.minimum(ids, A - 1)
+    else:
+        ids = np.zeros(R, dtype=np.int32)
+    ids[rng.random(R) < 0.03] = A
+    reqs["adapter_id"] = ids
+    reqs["flags"] = (rng.random(R) < 0.5).astype(np.uint32)
+    reqs["rand_key"] = rng.integers(0, 1 << 64, size=R, dtype=np.uint64)
+    return reqs
+
+
+def algorithmic_bytes(R: int, P: int, A: int) -> int:
+    """24 R + 16 P + 4 A ceil(P/32)  (SURVEY.md section 8d)."""
+    return 24 * R + 16 * P + 4 * A * ((P + 31) // 32)
