@@ -1,0 +1,418 @@
+#!/usr/bin/env python3
+"""bench.py — routing decisions/s of the scheduler hot path on B200, against the HBM roofline.
+
+A "step" is one pass of the hot path over one batch of R synthetic request descriptors against a
+resident P-pod / A-adapter snapshot.  Default workload at N=1: BASELINE.json configs[3] run on one
+GPU (R = 2^20, P = 4096, A = 1024) — the configuration the 1/2/4/8-GPU metric is quoted on; it
+fits one GPU.  With N GPUs every rank schedules its own R-request shard of the same step against
+the NCCL-broadcast snapshot (weak scaling, no data-path collective).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload C4|C3|C2|C5] [--requests-per-gpu R]
+
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+from llm_instance_gateway_b200 import workload as WL  # noqa: E402
+
+METRIC = "routing decisions/sec (RxP batch)"
+UNIT = "decisions/s"
+L2_BYTES = 126 * 1024 * 1024
+FALLBACK_HBM_GBS = 6650.0     # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C4", choices=["C2", "C3", "C4", "C5"])
+    ap.add_argument("--requests-per-gpu", type=int, default=0,
+                    help="override R per GPU (default: the workload's R)")
+    ap.add_argument("--min-seconds", type=float, default=1.0,
+                    help="repeat the K-step timed region until this much device time has been "
+                         "spent, so the clock sampler sees the load; the median repeat is reported")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=10.0, help="target CPU time of the baseline sample")
+    return ap.parse_args()
+
+
+def hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def committed_traffic(workload):
+    """DRAM bytes per launch of the pick kernel from the committed ncu --set full capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            return json.load(fh).get(workload)
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi clock/throttle sampler running during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index: int):
+        self.idx = device_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(power)}
+
+
+# ---------------------------------------------------------------------------------------------------
+def cpu_reference_rate(snap, reqs, seed, nthreads, seconds):
+    """Time the oracle port (the reference's algorithm and data structures, in C) on a bounded
+    sample of the workload.  Returns (decisions/s, sample size)."""
+    from oracle import binding as oracle
+    pool = oracle.Pool(snap.pod_records())
+    names = snap.adapter_names()
+    probe = min(len(reqs), max(256, 64 * nthreads))
+    t0 = time.perf_counter()
+    pool.schedule_batch(names, WL.UNKNOWN_MODEL, np.ascontiguousarray(reqs[:probe]), seed, False, nthreads)
+    dt = max(time.perf_counter() - t0, 1e-6)
+    sample = int(min(len(reqs), max(probe, probe / dt * seconds)))
+    t0 = time.perf_counter()
+    pool.schedule_batch(names, WL.UNKNOWN_MODEL, np.ascontiguousarray(reqs[:sample]), seed, False, nthreads)
+    dt = time.perf_counter() - t0
+    return sample / dt, sample
+
+
+def run_reference(args, cfg, R):
+    """--impl reference: the reference's CPU algorithm (oracle port; the Go original cannot be
+    built in this image) on the host cores, each step a bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import binding as oracle
+    nthreads = oracle.hardware_threads()
+    snap = WL.make_snapshot(cfg["P"], cfg["A"])
+    reqs = WL.make_requests(min(R, 1 << 18), cfg["A"])
+    pool = oracle.Pool(snap.pod_records())
+    names = snap.adapter_names()
+    probe = min(len(reqs), 64 * nthreads)
+    t0 = time.perf_counter()
+    pool.schedule_batch(names, WL.UNKNOWN_MODEL, np.ascontiguousarray(reqs[:probe]), 1, False, nthreads)
+    rate = probe / max(time.perf_counter() - t0, 1e-6)
+    budget = 60.0
+    S = int(max(16 * nthreads, min(len(reqs), rate * budget / (args.steps + args.warmup))))
+    chunks = [np.ascontiguousarray(reqs[(i * S) % (len(reqs) - S + 1):][:S]) for i in range(args.steps + args.warmup)]
+    for i in range(args.warmup):
+        pool.schedule_batch(names, WL.UNKNOWN_MODEL, chunks[i], i, False, nthreads)
+    t0 = time.perf_counter()
+    for i in range(args.warmup, args.warmup + args.steps):
+        pool.schedule_batch(names, WL.UNKNOWN_MODEL, chunks[i], i, False, nthreads)
+    dt = time.perf_counter() - t0
+    value = S * args.steps / dt
+    sample = f"{S} requests per step drawn from the {args.workload} batch (P={cfg['P']}, A={cfg['A']})"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64+f64",
+        "data": "synthetic",
+        "config": {"workload": f"{args.workload}: R={R} requests/GPU x P={cfg['P']} pods, A={cfg['A']} adapters",
+                   "note": "C restatement of the Go scheduler (Go toolchain absent): same tree, pointer "
+                           "slices, string-keyed ActiveModels maps, fresh slice per stage; all host threads"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": nthreads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    cfg = dict(WL.CONFIGS[args.workload])
+    R = args.requests_per_gpu or cfg["R"]
+    if args.impl == "reference":
+        return run_reference(args, cfg, R)
+
+    import torch
+    import torch.distributed as dist
+
+    from llm_instance_gateway_b200.engine import Engine
+    from llm_instance_gateway_b200.packer import PICK_DTYPE
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    P, A = cfg["P"], cfg["A"]
+    K, Wm = args.steps, max(args.warmup, 3)
+
+    eng = Engine(local_rank, max_pods=max(P, 1), max_adapters=A, max_batch=R)
+    stream = torch.cuda.Stream()
+
+    # --- snapshot: rank 0 packs it, one NCCL broadcast replicates it (the only exchange step) ---
+    snap = WL.make_snapshot(P, A) if rank == 0 or world == 1 else None
+    nbytes = int(__import__("llm_instance_gateway_b200._native", fromlist=["x"]).load().lig_snapshot_bytes(P, A))
+    if rank == 0:
+        blob = torch.from_numpy(snap.packed.blob()).to(dev)
+    else:
+        blob = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    if world > 1:
+        dist.broadcast(blob, src=0)
+    epoch = 1
+    with torch.cuda.stream(stream):
+        eng.upload_snapshot_device(epoch, P, A, blob.data_ptr(), stream.cuda_stream)
+    stream.synchronize()
+
+    # --- resident request batches: more distinct bytes than L2 so no step re-reads a cached batch
+    nb = max(4, -(-2 * L2_BYTES // (R * 24)))
+    nb = min(nb, 64)
+    host_batches = [WL.make_requests(R, A, seed=WL.REQUEST_SEED + 1000 * rank + b) for b in range(min(nb, 8))]
+    d_reqs, d_out = [], []
+    for b in range(nb):
+        base = torch.from_numpy(host_batches[b % len(host_batches)].view(np.uint8).reshape(-1)).to(dev)
+        if b >= len(host_batches):       # derive further distinct batches on the device
+            v = base.view(torch.int64).clone()
+            v[1::2] ^= (0x9E3779B97F4A7C15 * (b + 1)) & 0x7FFFFFFFFFFFFFFF   # new rand_key
+            v = v.view(torch.uint8).view(-1, 16).roll(shifts=b * 7919, dims=0).contiguous()
+            base = v.view(-1)
+        d_reqs.append(base)
+        d_out.append(torch.zeros(R * 8, dtype=torch.uint8, device=dev))
+    req_ptrs = [t.data_ptr() for t in d_reqs]
+    out_ptrs = [t.data_ptr() for t in d_out]
+
+    def launch_steps(first, count, seed0):
+        idx = [(first + i) % nb for i in range(count)]
+        eng.schedule_batches_device(epoch, seed0, [req_ptrs[i] for i in idx], R, [out_ptrs[i] for i in idx],
+                                    stream.cuda_stream)
+
+    # --- parity spot check on the exact bench inputs (oracle = checker, not the thing measured) ---
+    parity_n = 0
+    if rank == 0:
+        from oracle import binding as oracle
+        parity_n = min(R, 4096)
+        with torch.cuda.stream(stream):
+            launch_steps(0, 1, 123)
+        stream.synchronize()
+        got = d_out[0][: parity_n * 8].cpu().numpy().view(PICK_DTYPE)
+        want, _ = oracle.Pool(snap.pod_records()).schedule_batch(
+            snap.adapter_names(), WL.UNKNOWN_MODEL, np.ascontiguousarray(host_batches[0][:parity_n]), 123)
+        if not np.array_equal(got, want):
+            raise SystemExit("bench inputs: GPU picks differ from the oracle — refusing to time a wrong kernel")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # --- device-resident throughput (value) -------------------------------------------------------
+    with torch.cuda.stream(stream):
+        launch_steps(0, Wm, 1)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = eng.kernel_launches
+    times, reps, spent = [], 0, 0.0
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    while True:
+        barrier()
+        with torch.cuda.stream(stream):
+            ev0.record(stream)
+            launch_steps(reps * K, K, 1000 + reps)
+            ev1.record(stream)
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        times.append(float(t.item()))
+        spent += times[-1] / 1e3
+        reps += 1
+        stop = torch.tensor([1 if (spent >= args.min_seconds or reps >= 2000) else 0], device=dev)
+        if world > 1:
+            dist.broadcast(stop, src=0)
+        if int(stop.item()):
+            break
+    launches_per_region = (eng.kernel_launches - launches0) // reps
+    ms_region = float(np.median(times))
+    value = world * R * K / (ms_region / 1e3)
+
+    # --- snapshot refresh cost and the every-step-rebuild variant --------------------------------
+    with torch.cuda.stream(stream):
+        for i in range(3):
+            eng.upload_snapshot_device(epoch, P, A, blob.data_ptr(), stream.cuda_stream)
+        ev0.record(stream)
+        for i in range(20):
+            eng.upload_snapshot_device(epoch, P, A, blob.data_ptr(), stream.cuda_stream)
+        ev1.record(stream)
+    barrier()
+    snapshot_build_us = ev0.elapsed_time(ev1) / 20 * 1e3
+    with torch.cuda.stream(stream):
+        ev0.record(stream)
+        for i in range(min(K, 50)):
+            eng.upload_snapshot_device(epoch, P, A, blob.data_ptr(), stream.cuda_stream)
+            launch_steps(i, 1, 5000 + i)
+        ev1.record(stream)
+    barrier()
+    t = torch.tensor([ev0.elapsed_time(ev1) / min(K, 50)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    value_rebuild = world * R / (float(t.item()) / 1e3)
+
+    # --- direct-scan kernel (per-request tree walk, no class tables): secondary figure -------------
+    Rs = min(R, 1 << 15)
+    with torch.cuda.stream(stream):
+        eng.schedule_scan_device(epoch, 1, req_ptrs[0], Rs, out_ptrs[0], 0, stream.cuda_stream)
+        ev0.record(stream)
+        for i in range(3):
+            eng.schedule_scan_device(epoch, 2 + i, req_ptrs[1 % nb], Rs, out_ptrs[1 % nb], 0, stream.cuda_stream)
+        ev1.record(stream)
+    barrier()
+    scan_ms = ev0.elapsed_time(ev1) / 3
+    scan_value = Rs / (scan_ms / 1e3)
+
+    # --- e2e: host buffers through the public C-ABI call, snapshot refresh included every step ----
+    lib_reqs = [torch.from_numpy(hb.view(np.uint8).reshape(-1)).pin_memory() for hb in host_batches[:4]]
+    pin_out = torch.zeros(R * 8, dtype=torch.uint8).pin_memory()
+    if rank == 0 or world == 1:
+        packed = snap.packed
+    else:
+        packed = WL.make_snapshot(P, A).packed
+    e2e_steps = max(3, min(K, 50))
+    for i in range(3):
+        eng.upload_snapshot(epoch + 1, packed)
+        eng.schedule_batch_ptr(epoch + 1, i, lib_reqs[i % len(lib_reqs)].data_ptr(), R, pin_out.data_ptr())
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        eng.upload_snapshot(epoch + 1, packed)        # the 50 ms refresh tick, charged to every step
+        eng.schedule_batch_ptr(epoch + 1, 100 + i, lib_reqs[i % len(lib_reqs)].data_ptr(), R, pin_out.data_ptr())
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * R * e2e_steps / float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank == 0:
+        peak, peak_src = hbm_peak()
+        alg_bytes = WL.algorithmic_bytes(R, P, A)
+        launch_s = ms_region / 1e3 / K
+        achieved = alg_bytes / launch_s / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
+            "ms_per_step": ms_region / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int32/u64 index arithmetic + f64 compares", "data": "synthetic",
+            "config": {
+                "workload": f"{args.workload}: R={R} requests/GPU/step x P={P} pods, A={A} adapters "
+                            f"(BASELINE.json configs[{ {'C2': 1, 'C3': 2, 'C4': 3, 'C5': 4}[args.workload] }])",
+                "requests_per_gpu": R, "pods": P, "adapters": A, "parallelism": f"request-sharded x{world}",
+                "l2": f"{nb} distinct resident batches ({nb * R * 24 / 2**20:.0f} MiB in+out) cycled: "
+                      "inputs larger than the 126 MB L2",
+                "timed_region_repeats": reps, "region_ms_min_med_max": [min(times), ms_region, max(times)],
+                "snapshot": "resident (tables built at upload, once per refresh tick); see with_snapshot_rebuild",
+            },
+            "e2e": {"value": e2e_value, "unit": UNIT,
+                    "h2d_bytes_per_step": 16 * R + nbytes, "d2h_bytes_per_step": 8 * R,
+                    "steps": e2e_steps,
+                    "note": "lig_upload_snapshot + lig_schedule_batch per step, pinned host buffers"},
+            "gpu_launches": int(launches_per_region),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": committed_traffic(args.workload),
+                         "kernel": "lig_pick_stream_kernel", "algorithmic_bytes_per_launch": alg_bytes,
+                         "launch_us": launch_s * 1e6, "peak_source": peak_src},
+            "clocks": clocks,
+            "snapshot_build_us": snapshot_build_us,
+            "with_snapshot_rebuild": {"value": value_rebuild, "unit": UNIT,
+                                      "note": "every step re-uploads the snapshot and rebuilds all class tables"},
+            "direct_scan": {"value": scan_value, "unit": UNIT, "pod_evals_per_s": scan_value * P,
+                            "requests": Rs, "note": "lig_scan_kernel: per-request tree walk, no class tables"},
+            "parity_checked": parity_n,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import binding as oracle
+            nthreads = oracle.hardware_threads()
+            v, sample = cpu_reference_rate(snap, host_batches[0], 123, nthreads, args.cpu_seconds)
+            v1, sample1 = cpu_reference_rate(snap, host_batches[0], 123, 1, min(args.cpu_seconds, 3.0))
+            line["cpu_baseline"] = {
+                "value": v, "unit": UNIT, "cores": nthreads, "kind": "port",
+                "sample": f"first {sample} requests of batch 0 of the same workload",
+                "single_thread": {"value": v1, "sample": sample1},
+                "note": "C restatement of the Go scheduler with the reference's data structures "
+                        "(Go toolchain absent from the image)"}
+        print(json.dumps(line))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

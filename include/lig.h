@@ -167,6 +167,15 @@ int lig_schedule_batch(lig_ctx* ctx, uint64_t epoch, uint64_t seed, const lig_re
 int lig_schedule_batch_device(lig_ctx* ctx, uint64_t epoch, uint64_t seed, const lig_req* d_reqs,
                               int R, lig_pick* d_out, void* stream);
 
+/* A queue of n_batches HBM-resident batches of R requests each against one epoch, enqueued
+ * back to back on `stream` with one pass through the ABI (the micro-batcher's flush of several
+ * pending batches).  Batch b uses seed `seed + b`, reads d_reqs[b] and writes d_out[b]; the two
+ * pointer arrays are host arrays of device pointers.  Equivalent to n_batches calls of
+ * lig_schedule_batch_device. */
+int lig_schedule_batches_device(lig_ctx* ctx, uint64_t epoch, uint64_t seed,
+                                const lig_req* const* d_reqs, int R, lig_pick* const* d_out,
+                                int n_batches, void* stream);
+
 /* Direct scan: every request walks the whole tree over all P pods itself (one warp per request,
  * no class tables).  d_masks, when not NULL, receives the survivor set of every request as
  * R x ceil(P/32) words (bit p%32 of word p/32 = pod p survives) — the GPU analogue of

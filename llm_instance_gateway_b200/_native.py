@@ -20,7 +20,7 @@ LIG_MAX_PODS, LIG_MAX_ADAPTERS = 32768, 65534
 EXPORTED_SYMBOLS = (
     "lig_create", "lig_destroy", "lig_set_thresholds", "lig_get_thresholds", "lig_snapshot_bytes",
     "lig_pack_pods", "lig_pack_snapshot", "lig_upload_snapshot", "lig_upload_snapshot_device",
-    "lig_schedule_batch", "lig_schedule_batch_device", "lig_schedule_scan_device",
+    "lig_schedule_batch", "lig_schedule_batch_device", "lig_schedule_batches_device", "lig_schedule_scan_device",
     "lig_schedule_scan", "lig_read_class", "lig_last_error", "lig_version", "lig_abi_version",
     "lig_device_count", "lig_kernel_launches", "lig_sm_count",
 )
@@ -73,6 +73,7 @@ def load() -> C.CDLL:
     lib.lig_upload_snapshot_device.argtypes = [vp, u64, i32, i32, vp, vp]
     lib.lig_schedule_batch.argtypes = [vp, u64, u64, vp, i32, vp]
     lib.lig_schedule_batch_device.argtypes = [vp, u64, u64, vp, i32, vp, vp]
+    lib.lig_schedule_batches_device.argtypes = [vp, u64, u64, vp, i32, vp, i32, vp]
     lib.lig_schedule_scan_device.argtypes = [vp, u64, u64, vp, i32, vp, vp, vp]
     lib.lig_schedule_scan.argtypes = [vp, u64, u64, vp, i32, vp, vp]
     lib.lig_read_class.argtypes = [vp, u64, i32, i32, C.POINTER(i32), C.POINTER(i32), vp]

@@ -9,6 +9,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -92,6 +93,11 @@ struct lig_ctx {
   lig_pick* h_out = nullptr;
   std::atomic<uint64_t> launches{0};
   std::mutex mu;
+  // tuning knobs (env LIG_PICK_PER_THREAD = 1|2|4, LIG_QUEUE_STREAMS = 1..3), read at create
+  int pick_per_thread = 2;
+  int queue_streams = 2;
+  cudaEvent_t fork = nullptr;
+  cudaEvent_t join[kPipeStreams] = {};
 };
 
 namespace {
@@ -164,11 +170,23 @@ int launch_class_build(lig_ctx* c, Slot& s, cudaStream_t stream) {
 int launch_pick(lig_ctx* c, const Slot& s, uint64_t seed, const lig_req* d_reqs, int R,
                 lig_pick* d_out, cudaStream_t stream) {
   if (R == 0) return 0;
-  const int per_cta = kPickThreads * kPickPerThread;
+  const int4* in = reinterpret_cast<const int4*>(d_reqs);
+  int2* out = reinterpret_cast<int2*>(d_out);
+  const uint2* cls = reinterpret_cast<const uint2*>(s.d_cls);
+  const int stride = s.P > 0 ? s.P : 1;
+  const int per_cta = kPickThreads * c->pick_per_thread;
   const int grid = (R + per_cta - 1) / per_cta;
-  lig_pick_stream_kernel<<<grid, kPickThreads, 0, stream>>>(
-      reinterpret_cast<const int4*>(d_reqs), reinterpret_cast<int2*>(d_out), R,
-      reinterpret_cast<const uint2*>(s.d_cls), s.d_lists, s.P > 0 ? s.P : 1, s.A, seed);
+  switch (c->pick_per_thread) {
+    case 1:
+      lig_pick_stream_kernel<1><<<grid, kPickThreads, 0, stream>>>(in, out, R, cls, s.d_lists, stride, s.A, seed);
+      break;
+    case 2:
+      lig_pick_stream_kernel<2><<<grid, kPickThreads, 0, stream>>>(in, out, R, cls, s.d_lists, stride, s.A, seed);
+      break;
+    default:
+      lig_pick_stream_kernel<4><<<grid, kPickThreads, 0, stream>>>(in, out, R, cls, s.d_lists, stride, s.A, seed);
+      break;
+  }
   CUDA_TRY(cudaGetLastError());
   c->launches++;
   return 0;
@@ -320,6 +338,16 @@ static int create_impl(lig_ctx* c, int device, int max_pods, int max_adapters, i
     CUDA_TRY(cudaEventCreateWithFlags(&s.ready, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&s.idle, cudaEventDisableTiming));
   }
+  if (const char* e = getenv("LIG_PICK_PER_THREAD")) {
+    int v2 = atoi(e);
+    if (v2 == 1 || v2 == 2 || v2 == 4) c->pick_per_thread = v2;
+  }
+  if (const char* e = getenv("LIG_QUEUE_STREAMS")) {
+    int v2 = atoi(e);
+    if (v2 >= 1 && v2 <= kPipeStreams) c->queue_streams = v2;
+  }
+  CUDA_TRY(cudaEventCreateWithFlags(&c->fork, cudaEventDisableTiming));
+  for (auto& ev : c->join) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   CUDA_TRY(cudaStreamCreateWithFlags(&c->s_up, cudaStreamNonBlocking));
   for (auto& s : c->s_pipe) CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
   CUDA_TRY(cudaMalloc(&c->d_reqs, (size_t)max_batch * sizeof(lig_req)));
@@ -370,6 +398,9 @@ void lig_destroy(lig_ctx* c) {
     if (s.ready) cudaEventDestroy(s.ready);
     if (s.idle) cudaEventDestroy(s.idle);
   }
+  if (c->fork) cudaEventDestroy(c->fork);
+  for (auto& ev : c->join)
+    if (ev) cudaEventDestroy(ev);
   if (c->s_up) cudaStreamDestroy(c->s_up);
   for (auto& s : c->s_pipe)
     if (s) cudaStreamDestroy(s);
@@ -463,6 +494,43 @@ int lig_schedule_batch_device(lig_ctx* c, uint64_t epoch, uint64_t seed, const l
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CUDA_TRY(cudaStreamWaitEvent(st, s->ready, 0));
   if (int rc = launch_pick(c, *s, seed, d_reqs, R, d_out, st)) return rc;
+  CUDA_TRY(cudaEventRecord(s->idle, st));
+  return 0;
+}
+
+int lig_schedule_batches_device(lig_ctx* c, uint64_t epoch, uint64_t seed,
+                                const lig_req* const* d_reqs, int R, lig_pick* const* d_out,
+                                int n_batches, void* stream) {
+  if (!c || R < 0 || n_batches < 0 || (n_batches > 0 && (!d_reqs || !d_out)))
+    return fail(LIG_ERR_INVALID, "lig_schedule_batches_device: bad argument");
+  std::lock_guard<std::mutex> lk(c->mu);
+  Slot* s = nullptr;
+  if (int rc = resolve_slot(c, epoch, &s)) return rc;
+  if (n_batches == 0) return 0;
+  CUDA_TRY(cudaSetDevice(c->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUDA_TRY(cudaStreamWaitEvent(st, s->ready, 0));
+  for (int b = 0; b < n_batches; ++b)
+    if (R > 0 && (!d_reqs[b] || !d_out[b]))
+      return fail(LIG_ERR_INVALID, "lig_schedule_batches_device: null buffer in batch %d", b);
+  // Independent batches may overlap on the device: fork the caller's stream into the ctx's
+  // queue streams round-robin and join back, so the tail of batch b overlaps the head of b+1
+  // while everything stays ordered with respect to `stream`.
+  const int ns = (n_batches > 1) ? c->queue_streams : 1;
+  if (ns == 1) {
+    for (int b = 0; b < n_batches; ++b)
+      if (int rc = launch_pick(c, *s, seed + (uint64_t)b, d_reqs[b], R, d_out[b], st)) return rc;
+  } else {
+    CUDA_TRY(cudaEventRecord(c->fork, st));
+    for (int k = 0; k < ns; ++k) CUDA_TRY(cudaStreamWaitEvent(c->s_pipe[k], c->fork, 0));
+    for (int b = 0; b < n_batches; ++b)
+      if (int rc = launch_pick(c, *s, seed + (uint64_t)b, d_reqs[b], R, d_out[b], c->s_pipe[b % ns]))
+        return rc;
+    for (int k = 0; k < ns; ++k) {
+      CUDA_TRY(cudaEventRecord(c->join[k], c->s_pipe[k]));
+      CUDA_TRY(cudaStreamWaitEvent(st, c->join[k], 0));
+    }
+  }
   CUDA_TRY(cudaEventRecord(s->idle, st));
   return 0;
 }

@@ -385,23 +385,23 @@ lig_class_build_kernel(SnapView s, Thr thr, ClassEntry* __restrict__ cls,
 
 // ---- K2b: the streaming pick -----------------------------------------------------------------------
 // kPerThread requests per thread, strided by the CTA size so that every warp-level load is 512
-// contiguous bytes and every store 256.
+// contiguous bytes and every store 256.  All loads of a thread are issued before the first use.
 constexpr int kPickThreads = 256;
-constexpr int kPickPerThread = 4;
 
+template <int kPerThread>
 __global__ void __launch_bounds__(kPickThreads)
 lig_pick_stream_kernel(const int4* __restrict__ reqs, int2* __restrict__ out, int R,
                        const uint2* __restrict__ cls, const uint16_t* __restrict__ lists,
                        int list_stride, int A, uint64_t seed) {
-  const int base = blockIdx.x * (kPickThreads * kPickPerThread) + threadIdx.x;
-  int4 r[kPickPerThread];
+  const int base = blockIdx.x * (kPickThreads * kPerThread) + threadIdx.x;
+  int4 r[kPerThread];
 #pragma unroll
-  for (int j = 0; j < kPickPerThread; ++j) {
+  for (int j = 0; j < kPerThread; ++j) {
     int i = base + j * kPickThreads;
     if (i < R) r[j] = ld_stream_int4(reqs + i);
   }
 #pragma unroll
-  for (int j = 0; j < kPickPerThread; ++j) {
+  for (int j = 0; j < kPerThread; ++j) {
     int i = base + j * kPickThreads;
     if (i >= R) continue;
     const int adapter = r[j].x;
@@ -414,7 +414,7 @@ lig_pick_stream_kernel(const int4* __restrict__ reqs, int2* __restrict__ out, in
     int pod = -1;
     if (n > 0) {
       uint32_t k = int31n(seed ^ key, n, e.y);
-      pod = (int)__ldg(lists + (size_t)c * list_stride + k);
+      pod = (int)__ldg(lists + (size_t)((uint32_t)c * (uint32_t)list_stride + k));
     }
     // lig_pick {int32 pod_idx; uint16 status; uint16 n_survivors}
     st_stream_int2(out + i, make_int2(pod, (int)((e.x >> 16) | (n << 16))));

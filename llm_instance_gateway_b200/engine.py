@@ -80,6 +80,16 @@ class Engine:
         N.check(self._lib.lig_schedule_batch_device(self._ctx, epoch, seed, d_reqs, R, d_out,
                                                     stream or None))
 
+    def schedule_batches_device(self, epoch: int, seed: int, d_reqs_ptrs, R: int, d_out_ptrs,
+                                stream: int = 0) -> None:
+        """Queue len(d_reqs_ptrs) resident batches back to back (one pass through the ABI)."""
+        n = len(d_reqs_ptrs)
+        assert n == len(d_out_ptrs)
+        a = (C.c_void_p * n)(*d_reqs_ptrs)
+        b = (C.c_void_p * n)(*d_out_ptrs)
+        N.check(self._lib.lig_schedule_batches_device(self._ctx, epoch, seed, a, R, b, n,
+                                                      stream or None))
+
     def schedule_scan_device(self, epoch: int, seed: int, d_reqs: int, R: int, d_out: int,
                              d_masks: int = 0, stream: int = 0) -> None:
         N.check(self._lib.lig_schedule_scan_device(self._ctx, epoch, seed, d_reqs, R, d_out,

@@ -70,8 +70,10 @@ def pack_columns(kv, q64, n_active64, max_active64, bitmap, adapter_ids=None, po
     na = np.zeros(P, dtype=np.uint16)
     ma = np.zeros(P, dtype=np.uint16)
     N.check(lib.lig_pack_pods(P, _ptr(q64), _ptr(na64), _ptr(ma64), _ptr(q), _ptr(na), _ptr(ma)))
-    bitmap = np.ascontiguousarray(bitmap, dtype=np.uint32).reshape(-1, (P + 31) // 32)
-    A = int(bitmap.shape[0])
+    W = (P + 31) // 32
+    bitmap = np.ascontiguousarray(bitmap, dtype=np.uint32)
+    A = int(bitmap.shape[0]) if bitmap.ndim == 2 else (bitmap.size // W if W else 0)
+    bitmap = bitmap.reshape(A, W)
     return PackedSnapshot(P=P, A=A, kv=kv, q=q, n_active=na, max_active=ma, bitmap=bitmap,
                           adapter_ids=dict(adapter_ids or {}),
                           pods=list(pods) if pods is not None else [Pod(f"pod-{i}", f"address-{i}") for i in range(P)])

@@ -45,7 +45,7 @@ class SyntheticSnapshot:
     max_active64: np.ndarray     # the un-saturated Go-width value
     q64: np.ndarray
 
-    def oracle_pods(self) -> List[dict]:
+    def pod_records(self) -> List[dict]:
         p = self.packed
         return [dict(name=f"pod-{i}", address=f"address-{i}",
                      waiting_queue_size=int(self.q64[i]),
