@@ -157,8 +157,16 @@ int lig_upload_snapshot_device(lig_ctx* ctx, uint64_t epoch, int P, int A, const
  * and pod_idx is the k-th survivor in ascending pod index (= slice order, pods[i] scheduler.go:121).
  */
 
-/* Host buffers in, host buffers out: H2D copy, kernels, D2H copy, all inside the call
- * (chunk-pipelined on the ctx's own streams); blocks until `out` is complete. */
+/* Page-locked, device-mapped host memory for request / pick buffers (what the Go shim exposes
+ * to callers as unsafe.Slice).  Buffers from here (or any cudaHostAlloc /
+ * cudaHostRegister memory) are read and written by the kernel in place; ordinary pageable
+ * memory also works but bounces through the ctx's own pinned buffers. */
+void* lig_host_alloc(size_t bytes);
+void  lig_host_free(void* p);
+
+/* Host buffers in, host buffers out.  Nothing is staged through HBM: the pick kernel reads the
+ * descriptors from, and writes the picks to, page-locked host memory over PCIe directly.  Blocks
+ * until `out` is complete. */
 int lig_schedule_batch(lig_ctx* ctx, uint64_t epoch, uint64_t seed, const lig_req* reqs, int R,
                        lig_pick* out);
 

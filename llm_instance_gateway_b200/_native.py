@@ -22,7 +22,7 @@ EXPORTED_SYMBOLS = (
     "lig_pack_pods", "lig_pack_snapshot", "lig_upload_snapshot", "lig_upload_snapshot_device",
     "lig_schedule_batch", "lig_schedule_batch_device", "lig_schedule_batches_device", "lig_schedule_scan_device",
     "lig_schedule_scan", "lig_read_class", "lig_last_error", "lig_version", "lig_abi_version",
-    "lig_device_count", "lig_kernel_launches", "lig_sm_count",
+    "lig_device_count", "lig_kernel_launches", "lig_sm_count", "lig_host_alloc", "lig_host_free",
 )
 
 
@@ -82,6 +82,10 @@ def load() -> C.CDLL:
     lib.lig_kernel_launches.argtypes = [vp]
     lib.lig_kernel_launches.restype = u64
     lib.lig_sm_count.argtypes = [vp]
+    lib.lig_host_alloc.argtypes = [C.c_size_t]
+    lib.lig_host_alloc.restype = vp
+    lib.lig_host_free.argtypes = [vp]
+    lib.lig_host_free.restype = None
     for name in EXPORTED_SYMBOLS:
         getattr(lib, name)  # AttributeError if the library does not export it
     _lib = lib
