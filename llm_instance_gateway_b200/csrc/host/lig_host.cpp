@@ -1,0 +1,223 @@
+// lig_host.cpp — see lig_host.hpp.  Talks to the device only through the C ABI of include/lig.h.
+#include "lig_host.hpp"
+
+#include <algorithm>
+#include <cstring>
+#include <random>
+
+#include "../../../include/lig.h"
+
+namespace lig {
+namespace scheduling {
+
+namespace {
+
+Status Errorf(int code, const std::string& msg) { return Status{code, msg}; }
+
+Status LigFailure(const char* what) {
+  return Errorf(Internal, std::string(what) + ": " + lig_last_error());
+}
+
+// status.Errorf(codes.ResourceExhausted, ...) printed through %w            scheduler.go:87,117
+const char kDropInner[] =
+    "rpc error: code = ResourceExhausted desc = dropping request due to limited backend resources";
+
+inline uint64_t splitmix_next(uint64_t& s) {
+  uint64_t z = (s += 0x9E3779B97F4A7C15ull);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+}  // namespace
+
+Status NewScheduler(std::shared_ptr<PodMetricsProvider> pmp, const Options& opt,
+                    std::unique_ptr<Scheduler>* out) {
+  if (!pmp || !out) return Errorf(Internal, "NewScheduler: nil provider");
+  std::unique_ptr<Scheduler> s(new Scheduler());
+  s->pmp_ = std::move(pmp);
+  s->opt_ = opt;
+  if (lig_create(&s->ctx_, opt.device, opt.max_pods, opt.max_adapters, opt.max_batch) != 0)
+    return LigFailure("lig_create");
+  lig_thresholds t{opt.kv_cache_threshold, opt.queue_threshold_critical, opt.queueing_threshold_lora};
+  if (lig_set_thresholds(s->ctx_, &t) != 0) return LigFailure("lig_set_thresholds");
+  s->h_reqs_ = static_cast<lig_req*>(lig_host_alloc((size_t)opt.max_batch * sizeof(lig_req)));
+  s->h_picks_ = static_cast<lig_pick*>(lig_host_alloc((size_t)opt.max_batch * sizeof(lig_pick)));
+  if (!s->h_reqs_ || !s->h_picks_) return LigFailure("lig_host_alloc");
+  uint64_t seed = opt.seed;
+  if (seed == 0) {
+    std::random_device rd;
+    seed = ((uint64_t)rd() << 32) ^ rd();
+  }
+  s->seed_ = seed;
+  s->rng_state_ = seed ^ 0xD1B54A32D192ED03ull;
+  Status st = s->Refresh();
+  if (!st.ok()) return st;
+  s->batcher_ = std::thread(&Scheduler::BatcherLoop, s.get());
+  if (opt.refresh_interval.count() > 0) s->refresher_ = std::thread(&Scheduler::RefresherLoop, s.get());
+  *out = std::move(s);
+  return Status{};
+}
+
+Scheduler::~Scheduler() {
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    stop_ = true;
+  }
+  cv_.notify_all();
+  if (batcher_.joinable()) batcher_.join();
+  if (refresher_.joinable()) refresher_.join();
+  if (h_reqs_) lig_host_free(h_reqs_);
+  if (h_picks_) lig_host_free(h_picks_);
+  if (ctx_) lig_destroy(ctx_);
+}
+
+// One pack per refresh tick replaces the per-request AllPodMetrics() of scheduler.go:114-115.
+Status Scheduler::Refresh() {
+  std::lock_guard<std::mutex> rk(refresh_mu_);
+  auto pods = pmp_->AllPodMetrics();
+  const int P = (int)pods.size();
+  auto snap = std::make_shared<Snapshot>();
+  snap->pods.reserve(P);
+  std::vector<double> kv(P);
+  std::vector<int64_t> q(P), na(P), ma(P);
+  for (int p = 0; p < P; ++p) {
+    const backend::PodMetrics& pm = *pods[p];
+    snap->pods.push_back(pm.pod);
+    kv[p] = pm.metrics.KVCacheUsagePercent;
+    q[p] = pm.metrics.WaitingQueueSize;
+    na[p] = (int64_t)pm.metrics.ActiveModels.size();
+    ma[p] = pm.metrics.MaxActiveModels;
+    for (const auto& kvp : pm.metrics.ActiveModels)
+      snap->adapter_ids.emplace(kvp.first, (int)snap->adapter_ids.size());
+  }
+  const int A = (int)snap->adapter_ids.size();
+  const int W = (P + 31) / 32;
+  snap->A = A;
+  std::vector<uint32_t> bitmap((size_t)A * W, 0u);
+  for (int p = 0; p < P; ++p)
+    for (const auto& kvp : pods[p]->metrics.ActiveModels)
+      bitmap[(size_t)snap->adapter_ids[kvp.first] * W + (p >> 5)] |= 1u << (p & 31);
+  std::vector<int32_t> q32(P);
+  std::vector<uint16_t> na16(P), ma16(P);
+  if (lig_pack_pods(P, q.data(), na.data(), ma.data(), q32.data(), na16.data(), ma16.data()) != 0)
+    return LigFailure("lig_pack_pods");
+  snap->epoch = next_epoch_++;
+  if (lig_upload_snapshot(ctx_, snap->epoch, P, A, kv.data(), q32.data(), na16.data(), ma16.data(),
+                          bitmap.data()) != 0)
+    return LigFailure("lig_upload_snapshot");
+  {
+    std::lock_guard<std::mutex> lk(snap_mu_);
+    snap_ = std::move(snap);
+  }
+  std::lock_guard<std::mutex> sk(stats_mu_);
+  stats_.refreshes++;
+  return Status{};
+}
+
+void Scheduler::RefresherLoop() {
+  std::unique_lock<std::mutex> lk(mu_);
+  while (!stop_) {
+    cv_.wait_for(lk, opt_.refresh_interval, [&] { return stop_; });
+    if (stop_) break;
+    lk.unlock();
+    Refresh();   // a failed refresh keeps the previous snapshot, like a failed scrape keeps stale
+                 // metrics (backend/provider.go:151-156)
+    lk.lock();
+  }
+}
+
+Status Scheduler::Schedule(const LLMRequest& req, backend::Pod* targetPod) {
+  Waiter w;
+  w.req = &req;
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    if (stop_) return Errorf(Internal, "scheduler is shut down");
+    if (pending_.empty()) oldest_ = std::chrono::steady_clock::now();
+    pending_.push_back(&w);
+  }
+  cv_.notify_all();
+  w.done.wait(0, std::memory_order_acquire);
+  if (w.status.ok() && targetPod) *targetPod = std::move(w.pod);
+  return w.status;
+}
+
+void Scheduler::BatcherLoop() {
+  std::vector<Waiter*> batch;
+  std::unique_lock<std::mutex> lk(mu_);
+  for (;;) {
+    cv_.wait(lk, [&] { return stop_ || !pending_.empty(); });
+    if (pending_.empty() && stop_) break;
+    const auto deadline = oldest_ + opt_.batch_window;
+    cv_.wait_until(lk, deadline, [&] { return stop_ || (int)pending_.size() >= opt_.flush_size; });
+    batch.clear();
+    batch.swap(pending_);
+    lk.unlock();
+    Flush(batch);
+    lk.lock();
+  }
+}
+
+void Scheduler::Flush(std::vector<Waiter*>& batch) {
+  size_t done = 0;
+  while (done < batch.size()) {
+    const int n = (int)std::min(batch.size() - done, (size_t)opt_.max_batch);
+    std::shared_ptr<const Snapshot> snap;
+    Status failure;
+    int rc = 0;
+    for (int attempt = 0; attempt < 4; ++attempt) {
+      {
+        std::lock_guard<std::mutex> lk(snap_mu_);
+        snap = snap_;
+      }
+      for (int i = 0; i < n; ++i) {
+        const LLMRequest& r = *batch[done + i]->req;
+        auto it = snap->adapter_ids.find(r.ResolvedTargetModel);
+        // a model in no pod's ActiveModels: id A matches no pod, like a Go map miss (filter.go:170)
+        h_reqs_[i].adapter_id = it == snap->adapter_ids.end() ? snap->A : it->second;
+        h_reqs_[i].flags = r.Critical ? LIG_REQ_CRITICAL : 0u;
+        h_reqs_[i].rand_key = splitmix_next(rng_state_);
+      }
+      rc = lig_schedule_batch(ctx_, snap->epoch, seed_, h_reqs_, n, h_picks_);
+      if (rc != LIG_ERR_STALE_EPOCH) break;   // two refreshes raced past this batch: re-resolve
+      std::lock_guard<std::mutex> sk(stats_mu_);
+      stats_.stale_retries++;
+    }
+    if (rc != 0) failure = LigFailure("lig_schedule_batch");
+    for (int i = 0; i < n; ++i) {
+      Waiter* w = batch[done + i];
+      if (rc != 0) {
+        w->status = failure;
+      } else if (h_picks_[i].status == LIG_OK) {
+        w->pod = snap->pods[(size_t)h_picks_[i].pod_idx];          // pods[i].Pod  scheduler.go:121
+      } else if (h_picks_[i].status == LIG_DROP) {
+        w->status = Errorf(ResourceExhausted,                         // scheduler.go:117
+                           std::string("failed to apply filter, resulted 0 pods, this should never "
+                                       "happen: ") + kDropInner);
+      } else {
+        w->status = Errorf(Unknown, "failed to apply filter, resulted 0 pods, this should never "
+                                    "happen: %!w(<nil>)");
+      }
+    }
+    {
+      std::lock_guard<std::mutex> sk(stats_mu_);
+      stats_.scheduled += (uint64_t)n;
+      stats_.batches++;
+      stats_.max_batch = std::max<uint64_t>(stats_.max_batch, (uint64_t)n);
+    }
+    for (int i = 0; i < n; ++i) {
+      Waiter* w = batch[done + i];
+      w->done.store(1, std::memory_order_release);
+      w->done.notify_one();
+    }
+    done += (size_t)n;
+  }
+}
+
+Stats Scheduler::stats() const {
+  std::lock_guard<std::mutex> sk(stats_mu_);
+  return stats_;
+}
+
+}  // namespace scheduling
+}  // namespace lig

@@ -1,0 +1,177 @@
+// lig_host.hpp — native host side above the C ABI (include/lig.h): the C++ counterpart of the Go
+// adapter a maintainer adds to the reference.  It mirrors the reference's
+// scheduling-package interface for the hot path — same names, argument meaning, error behaviour:
+//
+//   backend::Pod / Metrics / PodMetrics     pkg/ext-proc/backend/types.go:8-31
+//   scheduling::LLMRequest                   pkg/ext-proc/scheduling/types.go:4-11
+//   scheduling::PodMetricsProvider           pkg/ext-proc/scheduling/scheduler.go:108-110
+//   scheduling::NewScheduler / Scheduler     pkg/ext-proc/scheduling/scheduler.go:93-122
+//
+// Scheduler::Schedule is goroutine-style safe: many threads call it concurrently and block for
+// their pick (one caller per Envoy stream, pkg/ext-proc/handlers/request.go:72); a batcher thread
+// folds the concurrent calls into one lig_schedule_batch call per flush.  The snapshot is
+// re-packed once per refresh tick (refreshMetricsInterval, pkg/ext-proc/main.go:39) instead of
+// once per request.  No CPU scheduling path exists here: without liblig.so + a CUDA device,
+// NewScheduler fails.
+#pragma once
+
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <cstdint>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+struct lig_ctx;
+struct lig_req;
+struct lig_pick;
+
+namespace lig {
+
+namespace backend {
+
+struct Pod {                         // backend/types.go:8-11
+  std::string Name;
+  std::string Address;
+  std::string String() const { return Name + ":" + Address; }   // types.go:13-15
+};
+
+struct Metrics {                     // backend/types.go:17-26
+  std::map<std::string, int> ActiveModels;
+  int64_t MaxActiveModels = 0;
+  int64_t RunningQueueSize = 0;
+  int64_t WaitingQueueSize = 0;
+  double KVCacheUsagePercent = 0.0;
+  int64_t KvCacheMaxTokenCapacity = 0;
+};
+
+struct PodMetrics {                  // backend/types.go:28-31
+  Pod pod;
+  Metrics metrics;
+};
+
+}  // namespace backend
+
+namespace scheduling {
+
+struct LLMRequest {                  // scheduling/types.go:4-11
+  std::string Model;
+  std::map<std::string, int> TargetModels;
+  std::string ResolvedTargetModel;
+  bool Critical = false;
+};
+
+// google.golang.org/grpc/codes values the path can produce.
+enum Code : int { OK = 0, Unknown = 2, ResourceExhausted = 8, Internal = 13 };
+
+struct Status {                      // a Go `error` carrying a gRPC status code
+  int code = OK;
+  std::string message;
+  bool ok() const { return code == OK; }
+};
+
+class PodMetricsProvider {           // scheduling/scheduler.go:108-110
+ public:
+  virtual ~PodMetricsProvider() = default;
+  virtual std::vector<std::shared_ptr<const backend::PodMetrics>> AllPodMetrics() = 0;
+};
+
+struct Options {
+  int device = 0;
+  int max_pods = 4096;
+  int max_adapters = 1024;
+  int max_batch = 1 << 16;
+  // A batch is flushed when it has flush_size requests or its oldest request is batch_window old.
+  int flush_size = 4096;
+  std::chrono::microseconds batch_window{50};
+  uint64_t seed = 0;                 // 0 = seed from std::random_device (Go's auto-seeded source)
+  // >0: a refresher thread re-packs the provider's snapshot at this period.
+  std::chrono::milliseconds refresh_interval{0};
+  double kv_cache_threshold = 0.8;   // scheduler.go:15-24
+  int64_t queue_threshold_critical = 5;
+  int64_t queueing_threshold_lora = 50;
+};
+
+struct Stats {
+  uint64_t scheduled = 0;      // Schedule calls completed
+  uint64_t batches = 0;        // lig_schedule_batch calls issued
+  uint64_t max_batch = 0;      // largest batch flushed
+  uint64_t refreshes = 0;      // snapshots uploaded
+  uint64_t stale_retries = 0;  // batches re-resolved after LIG_ERR_STALE_EPOCH
+};
+
+class Scheduler {
+ public:
+  ~Scheduler();
+  Scheduler(const Scheduler&) = delete;
+  Scheduler& operator=(const Scheduler&) = delete;
+
+  // Schedule finds the target pod based on metrics and the requested lora adapter.
+  // Returns OK and fills *targetPod, or: ResourceExhausted "dropping request due to limited
+  // backend resources" wrapped exactly like scheduler.go:117 (-> HTTP 429 at
+  // handlers/server.go:97-109); Unknown for the "resulted 0 pods" case; Internal for a
+  // batch-level (CUDA) failure.                                       scheduler.go:113-122
+  Status Schedule(const LLMRequest& req, backend::Pod* targetPod);
+
+  // Re-read the provider and upload a new snapshot epoch (call on every metrics refresh).
+  Status Refresh();
+
+  Stats stats() const;
+
+ private:
+  friend Status NewScheduler(std::shared_ptr<PodMetricsProvider>, const Options&,
+                             std::unique_ptr<Scheduler>*);
+  Scheduler() = default;
+
+  struct Snapshot {
+    uint64_t epoch = 0;
+    int A = 0;
+    std::unordered_map<std::string, int> adapter_ids;
+    std::vector<backend::Pod> pods;
+  };
+  struct Waiter {
+    const LLMRequest* req = nullptr;
+    Status status;
+    backend::Pod pod;
+    std::atomic<uint32_t> done{0};
+  };
+
+  void BatcherLoop();
+  void RefresherLoop();
+  void Flush(std::vector<Waiter*>& batch);
+
+  std::shared_ptr<PodMetricsProvider> pmp_;
+  Options opt_;
+  lig_ctx* ctx_ = nullptr;
+  lig_req* h_reqs_ = nullptr;      // pinned, device-mapped (lig_host_alloc)
+  lig_pick* h_picks_ = nullptr;
+  uint64_t seed_ = 0;
+  uint64_t rng_state_ = 0;
+
+  mutable std::mutex snap_mu_;
+  std::shared_ptr<const Snapshot> snap_;
+  uint64_t next_epoch_ = 1;
+  std::mutex refresh_mu_;
+
+  std::mutex mu_;
+  std::condition_variable cv_;
+  std::vector<Waiter*> pending_;
+  std::chrono::steady_clock::time_point oldest_;
+  bool stop_ = false;
+  std::thread batcher_, refresher_;
+
+  mutable std::mutex stats_mu_;
+  Stats stats_;
+};
+
+// NewScheduler                                                        scheduler.go:93-99
+Status NewScheduler(std::shared_ptr<PodMetricsProvider> pmp, const Options& opt,
+                    std::unique_ptr<Scheduler>* out);
+
+}  // namespace scheduling
+}  // namespace lig

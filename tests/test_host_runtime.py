@@ -1,0 +1,123 @@
+"""The native C++ host runtime (lig::scheduling::Scheduler, csrc/host/) above the C ABI."""
+import numpy as np
+import pytest
+
+from helpers import golden_to_podmetrics
+from llm_instance_gateway_b200 import host as H
+from llm_instance_gateway_b200 import workload as WL
+from llm_instance_gateway_b200 import _native as N
+from llm_instance_gateway_b200.backend import Metrics, Pod, PodMetrics
+
+
+def test_host_library_loads_and_exports():
+    lib = H.load()
+    for name in H.EXPORTED_SYMBOLS:
+        assert hasattr(lib, name)
+
+
+@pytest.mark.skipif(N.load().lig_device_count() > 0, reason="checks the no-GPU failure mode")
+def test_host_scheduler_fails_loudly_without_gpu():
+    prov = H.HostProvider([PodMetrics(Pod("p", "a"), Metrics())])
+    with pytest.raises(H.HostSchedulerError) as ei:
+        H.HostScheduler(prov, max_pods=8, max_adapters=8, max_batch=8)
+    assert "no CPU path" in str(ei.value)
+    prov.close()
+
+
+def snapshot_to_podmetrics(snap):
+    p = snap.packed
+    return [PodMetrics(Pod(f"pod-{i}", f"address-{i}"),
+                       Metrics(WaitingQueueSize=int(snap.q64[i]), KVCacheUsagePercent=float(p.kv[i]),
+                               MaxActiveModels=int(snap.max_active64[i]),
+                               ActiveModels={WL.adapter_name(a): 1 for a in snap.active[i]}))
+            for i in range(p.P)]
+
+
+@pytest.mark.gpu
+def test_golden_vectors_through_cpp_scheduler(golden):
+    for case in golden["TestFilter"]:
+        if case["filter"]["name"] != "defaultFilter":
+            continue
+        prov = H.HostProvider([golden_to_podmetrics(p) for p in case["input"]])
+        s = H.HostScheduler(prov, max_pods=64, max_adapters=64, max_batch=256)
+        req = case["req"]
+        code, pod, err = s.Schedule(req["model"], req["resolved_target_model"], req["critical"])
+        if case["err"]:
+            assert code == H.GRPC_RESOURCE_EXHAUSTED and pod is None
+            assert err == ("failed to apply filter, resulted 0 pods, this should never happen: rpc error: "
+                           "code = ResourceExhausted desc = dropping request due to limited backend resources")
+        else:
+            assert code == H.GRPC_OK and pod.Name == case["output"][0]["name"], case["name"]
+        s.close()
+        prov.close()
+    case = golden["TestHandleRequestBody"][0]
+    prov = H.HostProvider([golden_to_podmetrics(p) for p in case["pods"]])
+    s = H.HostScheduler(prov, max_pods=64, max_adapters=64, max_batch=256)
+    resolved = case["models"][case["request_model"]]["target_models"][0]["name"]
+    code, pod, _ = s.Schedule(case["request_model"], resolved, False)
+    assert code == 0 and pod.Address == "address-1" and pod.Name == "pod-1"
+    s.close()
+    prov.close()
+
+
+@pytest.mark.gpu
+def test_concurrent_callers_are_batched_and_correct(oracle):
+    P, A = 300, 24
+    snap = WL.make_snapshot(P, A, seed=31)
+    prov = H.HostProvider(snapshot_to_podmetrics(snap))
+    s = H.HostScheduler(prov, max_pods=512, max_adapters=64, max_batch=4096, flush_size=256, batch_window_us=200)
+    models = [WL.adapter_name(a) for a in range(A)] + [WL.UNKNOWN_MODEL]
+    models = models + models
+    critical = [False] * (A + 1) + [True] * (A + 1)
+    codes, pods = s.schedule_concurrent(64, 200, models, critical)
+    pool = oracle.Pool(snap.pod_records())
+    want = {}
+    for m, c in set(zip(models, critical)):
+        want[(m, c)] = pool.filter(m, c)
+    n = len(codes)
+    for i in range(n):
+        m, c = models[i % len(models)], critical[i % len(models)]
+        rc, survivors = want[(m, c)]
+        if rc == oracle.LIGO_OK:
+            assert codes[i] == H.GRPC_OK and pods[i] in survivors, (i, m, c)
+        elif rc == oracle.LIGO_DROP:
+            assert codes[i] == H.GRPC_RESOURCE_EXHAUSTED and pods[i] == -1
+        else:
+            assert codes[i] == H.GRPC_UNKNOWN
+    st = s.stats()
+    assert st["scheduled"] == n and st["batches"] < n / 4 and st["max_batch"] > 8, st
+    # every survivor of a multi-survivor class gets picked eventually (uniform draw)
+    big = max(want.items(), key=lambda kv: len(kv[1][1]))
+    if len(big[1][1]) > 1:
+        sel = [pods[i] for i in range(n) if (models[i % len(models)], critical[i % len(models)]) == big[0]]
+        assert set(sel) == set(big[1][1])
+    s.close()
+    prov.close()
+
+
+@pytest.mark.gpu
+def test_refresh_follows_the_provider():
+    mk = lambda q0, q1: [PodMetrics(Pod("pod-0", "address-0"), Metrics(WaitingQueueSize=q0, KVCacheUsagePercent=0.1)),
+                         PodMetrics(Pod("pod-1", "address-1"), Metrics(WaitingQueueSize=q1, KVCacheUsagePercent=0.1))]
+    prov = H.HostProvider(mk(0, 30))
+    s = H.HostScheduler(prov, max_pods=8, max_adapters=8, max_batch=64)
+    assert s.Schedule("m", "m", True)[1].Name == "pod-0"
+    prov.set_pods(mk(30, 0))
+    assert s.Schedule("m", "m", True)[1].Name == "pod-0"      # snapshot not refreshed yet
+    s.Refresh()
+    assert s.Schedule("m", "m", True)[1].Name == "pod-1"
+    prov.set_pods(mk(30, 30))                                   # nobody has capacity for sheddable
+    s.Refresh()
+    assert s.Schedule("m", "m", False)[0] == H.GRPC_RESOURCE_EXHAUSTED
+    assert s.Schedule("m", "m", True)[0] == H.GRPC_OK
+    assert s.stats()["refreshes"] == 3
+    s.close()
+    # background refresher thread
+    prov.set_pods(mk(0, 30))
+    s = H.HostScheduler(prov, max_pods=8, max_adapters=8, max_batch=64, refresh_interval_ms=5)
+    prov.set_pods(mk(30, 0))
+    import time
+    time.sleep(0.1)
+    assert s.Schedule("m", "m", True)[1].Name == "pod-1"
+    s.close()
+    prov.close()
