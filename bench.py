@@ -51,6 +51,8 @@ def parse_args():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: every GPU schedules R requests per step (default); strong: the "
                          "workload's R requests are sharded contiguously over the GPUs")
+    ap.add_argument("--timed-only", action="store_true",
+                    help="run only warm-up + the K-step timed region (for ncu launch lists)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="target CPU time of the baseline sample")
     return ap.parse_args()
@@ -305,6 +307,16 @@ def main():
     launches_per_region = (eng.kernel_launches - launches0) // reps
     ms_region = float(np.median(times))
     value = R_total * K / (ms_region / 1e3)
+
+    if args.timed_only:
+        if rank == 0:
+            sampler.stop()
+            print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
+                              "ms_per_step": ms_region / K, "timed_only": True}))
+        eng.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
 
     # --- snapshot refresh cost and the every-step-rebuild variant --------------------------------
     with torch.cuda.stream(stream):

@@ -97,6 +97,8 @@ struct lig_ctx {
   // tuning knobs (env LIG_PICK_PER_THREAD = 1|2|4, LIG_QUEUE_STREAMS = 1..3), read at create
   int pick_per_thread = 4;
   int queue_streams = 4;
+  bool use_pdl = false;  // env LIG_PDL=1: programmatic dependent launch inside batch queues
+  int prefetch_distance = 1;  // env LIG_PREFETCH=d (0 = off): batch b pulls batch b+d of the same queue into L2
   cudaEvent_t fork = nullptr;
   cudaEvent_t join[kPipeStreams] = {};
 };
@@ -150,26 +152,49 @@ bool staged_fits(const lig_ctx* c, int W) {
 int launch_class_build(lig_ctx* c, Slot& s, cudaStream_t stream) {
   const SnapView v = view_of(s);
   const int n_classes = 2 * (s.A + 1);
-  const int ctas_needed = (n_classes + kWarpsPerCta - 1) / kWarpsPerCta;
-  const bool staged = s.P > 0 && staged_fits(c, s.W);
-  const size_t smem = scratch_bytes(s.W > 0 ? s.W : 1) + (staged ? staged_bytes(s.W) : 0);
-  const int ctas_per_sm = staged ? (smem > 110 * 1024 ? 1 : 2) : 4;
-  int grid = ctas_needed < c->sm_count * ctas_per_sm ? ctas_needed : c->sm_count * ctas_per_sm;
+  const int W = s.W > 0 ? s.W : 1;
+  const bool staged = s.P > 0 && build_fixed_bytes(W) + staged_bytes(W) <= c->smem_optin;
+  const size_t smem = build_fixed_bytes(W) + (staged ? staged_bytes(W) : 0);
+  // every CTA repeats the shared stages, so no more CTAs than needed to give each warp a couple
+  // of classes, and never more than one per SM
+  int grid = (n_classes + 2 * kWarpsPerCta - 1) / (2 * kWarpsPerCta);
+  if (grid > c->sm_count) grid = c->sm_count;
   if (grid < 1) grid = 1;
+  const int stride = s.P > 0 ? s.P : 1;
   if (staged) {
-    lig_class_build_kernel<true><<<grid, kCtaThreads, smem, stream>>>(v, thr_of(c), s.d_cls,
-                                                                       s.d_lists, s.P > 0 ? s.P : 1);
+    lig_class_build_kernel<true><<<grid, kCtaThreads, smem, stream>>>(v, thr_of(c), s.d_cls, s.d_lists, stride);
   } else {
-    lig_class_build_kernel<false><<<grid, kCtaThreads, smem, stream>>>(v, thr_of(c), s.d_cls,
-                                                                        s.d_lists, s.P > 0 ? s.P : 1);
+    lig_class_build_kernel<false><<<grid, kCtaThreads, smem, stream>>>(v, thr_of(c), s.d_cls, s.d_lists, stride);
   }
   CUDA_TRY(cudaGetLastError());
   c->launches++;
   return 0;
 }
 
+template <int kPerThread>
+cudaError_t launch_pick_variant(int grid, cudaStream_t stream, bool overlap_prev, const int4* in,
+                                int2* out, int R, const uint2* cls, const uint16_t* lists,
+                                int stride, int A, uint64_t seed, const int4* prefetch) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kPickThreads);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = overlap_prev ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, lig_pick_stream_kernel<kPerThread>, in, out, R, cls, lists, stride, A,
+                            seed, prefetch);
+}
+
+// overlap_prev: the previous operation on `stream` is a pick kernel of the same queue call, whose
+// inputs and outputs this batch does not touch, so this grid may start before that one finished
+// (programmatic dependent launch; completion order on the stream is unchanged).
 int launch_pick(lig_ctx* c, const Slot& s, uint64_t seed, const lig_req* d_reqs, int R,
-                lig_pick* d_out, cudaStream_t stream) {
+                lig_pick* d_out, cudaStream_t stream, bool overlap_prev = false,
+                const lig_req* prefetch_reqs = nullptr) {
   if (R == 0) return 0;
   const int4* in = reinterpret_cast<const int4*>(d_reqs);
   int2* out = reinterpret_cast<int2*>(d_out);
@@ -177,21 +202,16 @@ int launch_pick(lig_ctx* c, const Slot& s, uint64_t seed, const lig_req* d_reqs,
   const int stride = s.P > 0 ? s.P : 1;
   const int per_cta = kPickThreads * c->pick_per_thread;
   const int grid = (R + per_cta - 1) / per_cta;
+  overlap_prev = overlap_prev && c->use_pdl;
+  const int4* pf = reinterpret_cast<const int4*>(prefetch_reqs);
+  cudaError_t e;
   switch (c->pick_per_thread) {
-    case 1:
-      lig_pick_stream_kernel<1><<<grid, kPickThreads, 0, stream>>>(in, out, R, cls, s.d_lists, stride, s.A, seed);
-      break;
-    case 2:
-      lig_pick_stream_kernel<2><<<grid, kPickThreads, 0, stream>>>(in, out, R, cls, s.d_lists, stride, s.A, seed);
-      break;
-    case 8:
-      lig_pick_stream_kernel<8><<<grid, kPickThreads, 0, stream>>>(in, out, R, cls, s.d_lists, stride, s.A, seed);
-      break;
-    default:
-      lig_pick_stream_kernel<4><<<grid, kPickThreads, 0, stream>>>(in, out, R, cls, s.d_lists, stride, s.A, seed);
-      break;
+    case 1: e = launch_pick_variant<1>(grid, stream, overlap_prev, in, out, R, cls, s.d_lists, stride, s.A, seed, pf); break;
+    case 2: e = launch_pick_variant<2>(grid, stream, overlap_prev, in, out, R, cls, s.d_lists, stride, s.A, seed, pf); break;
+    case 8: e = launch_pick_variant<8>(grid, stream, overlap_prev, in, out, R, cls, s.d_lists, stride, s.A, seed, pf); break;
+    default: e = launch_pick_variant<4>(grid, stream, overlap_prev, in, out, R, cls, s.d_lists, stride, s.A, seed, pf); break;
   }
-  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(e);
   c->launches++;
   return 0;
 }
@@ -333,15 +353,17 @@ static int create_impl(lig_ctx* c, int device, int max_pods, int max_adapters, i
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, v));
   CUDA_TRY(cudaFuncSetAttribute(lig_scan_kernel<false>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, v));
-  if (scratch_bytes(words_for(max_pods)) > c->smem_optin)
+  const size_t need = scratch_bytes(words_for(max_pods)) > build_fixed_bytes(words_for(max_pods))
+                          ? scratch_bytes(words_for(max_pods)) : build_fixed_bytes(words_for(max_pods));
+  if (need > c->smem_optin)
     return fail(LIG_ERR_INVALID, "max_pods=%d needs %zu B of per-CTA scratch, device allows %zu",
-                max_pods, scratch_bytes(words_for(max_pods)), c->smem_optin);
+                max_pods, need, c->smem_optin);
   const Layout l = layout_for(max_pods, max_adapters);
   const size_t n_classes = 2 * ((size_t)max_adapters + 1);
   for (auto& s : c->slot) {
     CUDA_TRY(cudaMalloc(&s.d_blob, l.total));
     CUDA_TRY(cudaMalloc(&s.d_cls, n_classes * sizeof(ClassEntry)));
-    CUDA_TRY(cudaMalloc(&s.d_lists, n_classes * (size_t)max_pods * sizeof(uint16_t)));
+    CUDA_TRY(cudaMalloc(&s.d_lists, (n_classes + 2) * (size_t)max_pods * sizeof(uint16_t)));
     CUDA_TRY(cudaHostAlloc(&s.h_blob, l.total, cudaHostAllocDefault));
     CUDA_TRY(cudaEventCreateWithFlags(&s.ready, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&s.idle, cudaEventDisableTiming));
@@ -349,6 +371,11 @@ static int create_impl(lig_ctx* c, int device, int max_pods, int max_adapters, i
   if (const char* e = getenv("LIG_PICK_PER_THREAD")) {
     int v2 = atoi(e);
     if (v2 == 1 || v2 == 2 || v2 == 4 || v2 == 8) c->pick_per_thread = v2;
+  }
+  if (const char* e = getenv("LIG_PDL")) c->use_pdl = atoi(e) != 0;
+  if (const char* e = getenv("LIG_PREFETCH")) {
+    int v2 = atoi(e);
+    if (v2 >= 0 && v2 <= 16) c->prefetch_distance = v2;
   }
   if (const char* e = getenv("LIG_QUEUE_STREAMS")) {
     int v2 = atoi(e);
@@ -525,14 +552,18 @@ int lig_schedule_batches_device(lig_ctx* c, uint64_t epoch, uint64_t seed,
   // queue streams round-robin and join back, so the tail of batch b overlaps the head of b+1
   // while everything stays ordered with respect to `stream`.
   const int ns = (n_batches > 1) ? c->queue_streams : 1;
+  const int pd = c->prefetch_distance;
   if (ns == 1) {
     for (int b = 0; b < n_batches; ++b)
-      if (int rc = launch_pick(c, *s, seed + (uint64_t)b, d_reqs[b], R, d_out[b], st)) return rc;
+      if (int rc = launch_pick(c, *s, seed + (uint64_t)b, d_reqs[b], R, d_out[b], st, b > 0,
+                               (pd > 0 && b + pd < n_batches) ? d_reqs[b + pd] : nullptr))
+        return rc;
   } else {
     CUDA_TRY(cudaEventRecord(c->fork, st));
     for (int k = 0; k < ns; ++k) CUDA_TRY(cudaStreamWaitEvent(c->s_pipe[k], c->fork, 0));
     for (int b = 0; b < n_batches; ++b)
-      if (int rc = launch_pick(c, *s, seed + (uint64_t)b, d_reqs[b], R, d_out[b], c->s_pipe[b % ns]))
+      if (int rc = launch_pick(c, *s, seed + (uint64_t)b, d_reqs[b], R, d_out[b], c->s_pipe[b % ns],
+                               b >= ns, (pd > 0 && b + pd < n_batches) ? d_reqs[b + pd] : nullptr))
         return rc;
     for (int k = 0; k < ns; ++k) {
       CUDA_TRY(cudaEventRecord(c->join[k], c->s_pipe[k]));
@@ -645,10 +676,11 @@ int lig_read_class(lig_ctx* c, uint64_t epoch, int critical, int adapter_id, int
   const int cls = (critical ? 1 : 0) * (s->A + 1) + a;
   ClassEntry e;
   CUDA_TRY(cudaMemcpy(&e, s->d_cls + cls, sizeof(e), cudaMemcpyDeviceToHost));
-  *n_survivors = (int)(e.n_status & 0xffffu);
-  *status = (int)(e.n_status >> 16);
+  *n_survivors = (int)entry_n(e.info);
+  *status = (int)entry_status(e.info);
   if (list && *n_survivors > 0)
-    CUDA_TRY(cudaMemcpy(list, s->d_lists + (size_t)cls * (s->P > 0 ? s->P : 1),
+    CUDA_TRY(cudaMemcpy(list, s->d_lists + (size_t)class_list_row(e.info, (uint32_t)cls, 2u * (uint32_t)(s->A + 1)) *
+                                               (size_t)(s->P > 0 ? s->P : 1),
                         (size_t)*n_survivors * sizeof(uint16_t), cudaMemcpyDeviceToHost));
   return 0;
 }

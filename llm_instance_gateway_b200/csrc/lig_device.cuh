@@ -1,8 +1,9 @@
 // lig_device.cuh — sm_100a device code of the endpoint picker.
 //
 // Three kernels, all integer / FP64-compare work (no tensor cores; HBM + issue bound):
-//   lig_class_build_kernel  one warp per request class (critical?, adapter): walks the reference's
-//                           filter tree over all P pods and writes the class's survivor list.
+//   lig_class_build_kernel  per snapshot: the adapter-independent stages of the reference's filter
+//                           tree once per CTA, then one warp per request class (critical?,
+//                           adapter) finishes the walk and writes the class's survivor list.
 //   lig_pick_stream_kernel  one thread per request: 16 B descriptor in, class lookup, Go Int31n
 //                           draw, one 2 B gather from the class list, 8 B result out.  The
 //                           bandwidth-bound stream the roofline is quoted on.
@@ -42,11 +43,29 @@ struct Thr {
   long long q_lora;   // queueingThresholdLoRA   scheduler.go:23
 };
 
-// One entry per request class c = critical * (A + 1) + min(adapter, A); 8 bytes.
+// One entry per request class c = critical * (A + 1) + min(adapter, A); 8 bytes (one uint2 load).
+// Classes whose survivor set does not depend on the adapter share one of two default lists
+// (rows 2(A+1) and 2(A+1)+1 of the list pool); the others own row c.  Row offsets are in list
+// entries and fit 32 bits: (2 * 65535 + 2) rows x 32768 entries < 2^32.
+//
+//   info : bits 0-1 status | 2-3 list row selector | 4-8 shift | 9 n is a power of two | 16-31 n
+//          (info & 0xffff0003 is the second word of lig_pick as is: status | n_survivors << 16)
+//   magic: M = ceil(2^(32+shift) / n), shift = ceil(log2 n) - 1, so that for every v < 2^31
+//          floor(v / n) == umulhi(v, M) >> shift   (Granlund-Montgomery, N = 31 bits; n >= 2)
+// With q = floor(v / n), Go's Int31n is k = v - q * n, resampling while v > 2^31-1-(2^31 % n),
+// i.e. while q >= floor(2^31 / n) = floor((2^31-1) / n) + (n is a power of two ? 1 : 0).
 struct ClassEntry {
-  uint32_t n_status;    // n_survivors | status << 16
-  uint32_t max_accept;  // Int31n's rejection bound 2^31 - 1 - (2^31 % n); 0xffffffff if n is 2^k
+  uint32_t info;
+  uint32_t magic;
 };
+enum : uint32_t { kRowOwn = 0, kRowCriticalDefault = 1, kRowSheddableDefault = 2 };
+
+__host__ __device__ inline uint32_t entry_n(uint32_t info) { return info >> 16; }
+__host__ __device__ inline uint32_t entry_status(uint32_t info) { return info & 3u; }
+__host__ __device__ inline uint32_t class_list_row(uint32_t info, uint32_t c, uint32_t n_classes) {
+  const uint32_t sel = (info >> 2) & 3u;
+  return sel == kRowOwn ? c : n_classes + sel - 1u;
+}
 
 // Pod metric columns as the tree walk reads them: either the snapshot in global memory (read
 // through the read-only path) or a copy the CTA staged into shared memory.
@@ -98,11 +117,26 @@ __device__ __forceinline__ uint32_t max_accept_for(uint32_t n) {
 }
 
 // rand.Intn(n) for 0 < n <= 2^31-1  ->  Int31n(n)          scheduler.go:120, math/rand Go 1.22
+// (plain form, used by the direct-scan kernel)
 __device__ __forceinline__ uint32_t int31n(uint64_t state, uint32_t n, uint32_t max_accept) {
   uint32_t v = splitmix_int31(state);
   if (max_accept == 0xffffffffu) return v & (n - 1);
   while (v > max_accept) v = splitmix_int31(state);
   return v % n;
+}
+
+// The same draw with the class entry's precomputed magic (no integer division on the hot path).
+__device__ __forceinline__ uint32_t int31n_magic(uint64_t state, uint32_t info, uint32_t magic) {
+  const uint32_t n = info >> 16;
+  const uint32_t shift = (info >> 4) & 31u;
+  const uint32_t q_limit = (__umulhi(0x7fffffffu, magic) >> shift) + ((info >> 9) & 1u);
+  uint32_t v = splitmix_int31(state);
+  uint32_t q = __umulhi(v, magic) >> shift;
+  while (q >= q_limit) {   // probability < n / 2^31 per draw
+    v = splitmix_int31(state);
+    q = __umulhi(v, magic) >> shift;
+  }
+  return n > 1u ? v - q * n : 0u;
 }
 
 // ---- one pass helpers; X is a per-warp mask of W words in shared memory -----------------------
@@ -339,46 +373,413 @@ __device__ __forceinline__ const uint32_t* stage_adapter_row(const SnapView& s, 
 }
 
 // ---- K2a: class tables ---------------------------------------------------------------------------
-// Class c = critical * (A + 1) + a, a in [0, A] (a == A: adapter active nowhere).  Writes
-// cls[c] and the survivors, ascending pod index, to lists[c * list_stride ...].
+// Class c = critical * (A + 1) + a, a in [0, A] (a == A: adapter active nowhere).
+//
+// Most of the tree does not depend on the adapter: the low-queue set, the
+// "has room" set, the sheddable-capacity set and the least-queuing stage that follows them are
+// the same for every class.  Each CTA therefore first walks those shared stages once with all 8
+// warps (dense, pod-parallel, ballot words), and a class then only costs one AND of its bitmap
+// row with a shared mask; only classes whose adapter actually intersects the mask run their own
+// range filters, on the (sparse) set bits.  Classes that do not intersect share one of two
+// default survivor lists.  lig_scan_kernel keeps the plain per-request walk (tree_eval_warp), so
+// the GPU holds two independent formulations of the tree, both checked against the oracle.
+
+struct BuildShared {        // block-wide scalars of the shared stages (shared memory)
+  uint32_t n_shed;          // |S|, S = {q <= q_crit && kv <= kv_thr}              scheduler.go:74-79
+  uint32_t crit_mode;       // 0: low-queue set non-empty; 1: empty (all pods go to queueLoRAAndKV)
+  uint32_t rc_n, rc_status; // default result of critical classes
+  uint32_t rs_n, rs_status; // default result of sheddable classes
+  uint32_t red_u[kWarpsPerCta];
+  int red_i[2 * kWarpsPerCta];
+  double red_d[2 * kWarpsPerCta];
+};
+
+__device__ __forceinline__ uint32_t blk_sum(uint32_t warp_value, BuildShared* sh, int warp, int lane) {
+  __syncthreads();
+  if (lane == 0) sh->red_u[warp] = warp_value;
+  __syncthreads();
+  uint32_t t = 0;
+#pragma unroll
+  for (int i = 0; i < kWarpsPerCta; ++i) t += sh->red_u[i];
+  return t;
+}
+
+// out[w] = ballot(member(in, w) && pred(p)) for all words, block-wide; returns the block count.
+template <class Pred>
+__device__ __forceinline__ uint32_t blk_pred_pass(uint32_t* out, const uint32_t* in, int P, int W,
+                                                  BuildShared* sh, int warp, int lane, Pred pred) {
+  uint32_t cnt = 0;
+  for (int w = warp; w < W; w += kWarpsPerCta) {
+    const int p = w * 32 + lane;
+    const bool member = in ? ((in[w] >> lane) & 1u) : (p < P);
+    const bool keep = member && pred(p);
+    const uint32_t nw = __ballot_sync(kFull, keep);
+    if (lane == 0) out[w] = nw;
+    cnt += __popc(nw);
+  }
+  return blk_sum(cnt, sh, warp, lane);
+}
+
+// leastQueuingFilterFunc over mask X (in place), block-wide.                 filter.go:102-122
+template <bool kStaged>
+__device__ __forceinline__ uint32_t blk_least_queuing(const Fields& f, uint32_t* X, int W, uint32_t n,
+                                                      BuildShared* sh, int warp, int lane) {
+  if (n == 0) return 0;
+  int mn = 0x7fffffff, mx = 0;
+  for (int w = warp; w < W; w += kWarpsPerCta) {
+    if ((X[w] >> lane) & 1u) {
+      const int v = ld_q<kStaged>(f, w * 32 + lane);
+      mn = min(mn, v);
+      mx = max(mx, v);
+    }
+  }
+  mn = __reduce_min_sync(kFull, mn);
+  mx = __reduce_max_sync(kFull, mx);
+  __syncthreads();
+  if (lane == 0) { sh->red_i[warp] = mn; sh->red_i[kWarpsPerCta + warp] = mx; }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < kWarpsPerCta; ++i) {
+    mn = min(mn, sh->red_i[i]);
+    mx = max(mx, sh->red_i[kWarpsPerCta + i]);
+  }
+  const uint32_t range = (uint32_t)mx - (uint32_t)mn;   // see stage_least_queuing
+  const long long thr = (long long)mn + (long long)(range / n);
+  uint32_t cnt = 0;
+  for (int w = warp; w < W; w += kWarpsPerCta) {
+    const uint32_t word = X[w];
+    bool keep = false;
+    if ((word >> lane) & 1u) {
+      const long long v = ld_q<kStaged>(f, w * 32 + lane);
+      keep = v >= (long long)mn && v <= thr;
+    }
+    const uint32_t nw = __ballot_sync(kFull, keep);
+    if (lane == 0) X[w] = nw;
+    cnt += __popc(nw);
+  }
+  return blk_sum(cnt, sh, warp, lane);
+}
+
+// leastKVCacheFilterFunc over mask X (in place), block-wide.                 filter.go:134-154
+template <bool kStaged>
+__device__ __forceinline__ uint32_t blk_least_kv(const Fields& f, uint32_t* X, int W, uint32_t n,
+                                                 BuildShared* sh, int warp, int lane) {
+  if (n == 0) return 0;
+  double mn = 1.7976931348623157e308, mx = 0.0;
+  for (int w = warp; w < W; w += kWarpsPerCta) {
+    if ((X[w] >> lane) & 1u) {
+      const double v = ld_kv<kStaged>(f, w * 32 + lane);
+      if (v <= mn) mn = v;
+      if (v >= mx) mx = v;
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    double o = __shfl_xor_sync(kFull, mn, off);
+    if (o < mn) mn = o;
+    o = __shfl_xor_sync(kFull, mx, off);
+    if (o > mx) mx = o;
+  }
+  __syncthreads();
+  if (lane == 0) { sh->red_d[warp] = mn; sh->red_d[kWarpsPerCta + warp] = mx; }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < kWarpsPerCta; ++i) {
+    const double a = sh->red_d[i], b = sh->red_d[kWarpsPerCta + i];
+    if (a < mn) mn = a;
+    if (b > mx) mx = b;
+  }
+  const double thr = __dadd_rn(mn, __ddiv_rn(__dsub_rn(mx, mn), (double)n));
+  uint32_t cnt = 0;
+  for (int w = warp; w < W; w += kWarpsPerCta) {
+    const uint32_t word = X[w];
+    bool keep = false;
+    if ((word >> lane) & 1u) {
+      const double v = ld_kv<kStaged>(f, w * 32 + lane);
+      keep = v >= mn && v <= thr;
+    }
+    const uint32_t nw = __ballot_sync(kFull, keep);
+    if (lane == 0) X[w] = nw;
+    cnt += __popc(nw);
+  }
+  return blk_sum(cnt, sh, warp, lane);
+}
+
+// The same two range filters for ONE warp on a sparse mask: lane l owns words l, l+32, ... and
+// walks their set bits.
+template <bool kStaged>
+__device__ __forceinline__ uint32_t sparse_least_queuing(const Fields& f, uint32_t* X, int W, int lane,
+                                                         uint32_t n) {
+  if (n == 0) return 0;
+  int mn = 0x7fffffff, mx = 0;
+  for (int w = lane; w < W; w += 32) {
+    uint32_t bits = X[w];
+    while (bits) {
+      const int b = __ffs(bits) - 1;
+      bits &= bits - 1;
+      const int v = ld_q<kStaged>(f, w * 32 + b);
+      mn = min(mn, v);
+      mx = max(mx, v);
+    }
+  }
+  mn = __reduce_min_sync(kFull, mn);
+  mx = __reduce_max_sync(kFull, mx);
+  const uint32_t range = (uint32_t)mx - (uint32_t)mn;
+  const long long thr = (long long)mn + (long long)(range / n);
+  uint32_t cnt = 0;
+  for (int w = lane; w < W; w += 32) {
+    uint32_t bits = X[w], nw = 0;
+    while (bits) {
+      const int b = __ffs(bits) - 1;
+      bits &= bits - 1;
+      const long long v = ld_q<kStaged>(f, w * 32 + b);
+      if (v >= (long long)mn && v <= thr) nw |= 1u << b;
+    }
+    X[w] = nw;
+    cnt += __popc(nw);
+  }
+  cnt = __reduce_add_sync(kFull, cnt);
+  __syncwarp();
+  return cnt;
+}
+
+template <bool kStaged>
+__device__ __forceinline__ uint32_t sparse_least_kv(const Fields& f, uint32_t* X, int W, int lane,
+                                                    uint32_t n) {
+  if (n == 0) return 0;
+  double mn = 1.7976931348623157e308, mx = 0.0;
+  for (int w = lane; w < W; w += 32) {
+    uint32_t bits = X[w];
+    while (bits) {
+      const int b = __ffs(bits) - 1;
+      bits &= bits - 1;
+      const double v = ld_kv<kStaged>(f, w * 32 + b);
+      if (v <= mn) mn = v;
+      if (v >= mx) mx = v;
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    double o = __shfl_xor_sync(kFull, mn, off);
+    if (o < mn) mn = o;
+    o = __shfl_xor_sync(kFull, mx, off);
+    if (o > mx) mx = o;
+  }
+  const double thr = __dadd_rn(mn, __ddiv_rn(__dsub_rn(mx, mn), (double)n));
+  uint32_t cnt = 0;
+  for (int w = lane; w < W; w += 32) {
+    uint32_t bits = X[w], nw = 0;
+    while (bits) {
+      const int b = __ffs(bits) - 1;
+      bits &= bits - 1;
+      const double v = ld_kv<kStaged>(f, w * 32 + b);
+      if (v >= mn && v <= thr) nw |= 1u << b;
+    }
+    X[w] = nw;
+    cnt += __popc(nw);
+  }
+  cnt = __reduce_add_sync(kFull, cnt);
+  __syncwarp();
+  return cnt;
+}
+
+// Write the set bits of X, ascending, to list[0..n): lane-strided words, warp prefix per 32 words.
+__device__ __forceinline__ void compact_mask_to_list(const uint32_t* X, int W, int lane,
+                                                     uint16_t* __restrict__ list) {
+  uint32_t base = 0;
+  for (int w0 = 0; w0 < W; w0 += 32) {
+    const int w = w0 + lane;
+    uint32_t bits = w < W ? X[w] : 0u;
+    const uint32_t c = __popc(bits);
+    uint32_t incl = c;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const uint32_t o = __shfl_up_sync(kFull, incl, off);
+      if (lane >= off) incl += o;
+    }
+    uint32_t pos = base + incl - c;
+    while (bits) {
+      const int b = __ffs(bits) - 1;
+      bits &= bits - 1;
+      list[pos++] = (uint16_t)(w * 32 + b);
+    }
+    base += __shfl_sync(kFull, incl, 31);
+  }
+}
+
+// Shared-memory carve-up of the class build:
+//   [ BuildShared ][ 6 block masks x W ][ per-warp scratch kWarpsPerCta x W ][ staged columns ]
+__host__ __device__ inline size_t build_fixed_bytes(int W) {
+  const size_t b = ((sizeof(BuildShared) + 15) & ~(size_t)15) +
+                   (size_t)(6 + kWarpsPerCta) * (size_t)W * sizeof(uint32_t);
+  return (b + 15) & ~(size_t)15;   // the staged columns behind it are written with 16-byte stores
+}
+
+__device__ __forceinline__ ClassEntry make_entry(uint32_t n, uint32_t status, uint32_t row_sel) {
+  ClassEntry e;
+  // n <= 1: magic 0 gives q = 0 for every draw; the power-of-two bit makes the rejection limit 1,
+  // so the first draw is always accepted and k = 0.
+  uint32_t shift = 0, magic = 0, pow2 = 1;
+  if (n >= 2) {
+    const uint32_t l = 32u - (uint32_t)__clz(n - 1u);          // ceil(log2 n), 1..15
+    shift = l - 1u;
+    pow2 = (n & (n - 1u)) == 0u;
+    // ceil(2^(32+shift) / n) < 2^32 because n > 2^(l-1)
+    magic = (uint32_t)((((unsigned long long)1 << (32u + shift)) + n - 1u) / n);
+  }
+  e.info = status | (row_sel << 2) | (shift << 4) | (pow2 << 9) | (n << 16);
+  e.magic = magic;
+  return e;
+}
+
 template <bool kStaged>
 __global__ void __launch_bounds__(kCtaThreads)
 lig_class_build_kernel(SnapView s, Thr thr, ClassEntry* __restrict__ cls,
                        uint16_t* __restrict__ lists, int list_stride) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint32_t* X = reinterpret_cast<uint32_t*>(smem) + (size_t)warp * 3 * s.W;
-  uint32_t* T = X + s.W;
-  uint32_t* H = T + s.W;
+  const int P = s.P, W = s.W, A = s.A;
+  BuildShared* sh = reinterpret_cast<BuildShared*>(smem);
+  uint32_t* masks = reinterpret_cast<uint32_t*>(smem + ((sizeof(BuildShared) + 15) & ~(size_t)15));
+  uint32_t* M_room = masks;            // n_active < max_active                       filter.go:175-177
+  uint32_t* CB = masks + 1 * W;        // critical: mask the adapter row is ANDed with
+  uint32_t* CZ = masks + 2 * W;        // critical mode 1: (least-queuing set) & room
+  uint32_t* SB = masks + 3 * W;        // sheddable: (least-queuing set of S) & ~room
+  uint32_t* SZ = masks + 4 * W;        // sheddable: (least-queuing set of S) & room
+  uint32_t* TMP = masks + 5 * W;
+  uint32_t* X = masks + (size_t)(6 + warp) * W;   // per-warp scratch
   Fields f{s.kv, s.q, s.n_active, s.max_active};
   if constexpr (kStaged) {
-    f = stage_fields(s, smem + scratch_bytes(s.W));
+    f = stage_fields(s, smem + build_fixed_bytes(W));
+  }
+  __syncthreads();
+  const int n_classes = 2 * (A + 1);
+  const uint32_t rc_row = (uint32_t)n_classes * (uint32_t)list_stride;        // default list rows
+  const uint32_t rs_row = rc_row + (uint32_t)list_stride;
+
+  if (P == 0) {   // critical: predicate node errs on an empty pool -> sheddable branch -> drop
+    for (int c = blockIdx.x * kCtaThreads + threadIdx.x; c < n_classes; c += gridDim.x * kCtaThreads)
+      cls[c] = make_entry(0u, (uint32_t)LIG_DROP, kRowOwn);
+    return;
+  }
+
+  // ---- shared stages (every CTA, all 8 warps) -------------------------------------------------
+  auto ldq = [&](int p) { return (long long)ld_q<kStaged>(f, p); };
+  blk_pred_pass(M_room, nullptr, P, W, sh, warp, lane, [&](int p) { return has_room<kStaged>(f, p); });
+  // critical side: "low queueing filter"                                  scheduler.go:58-60
+  const uint32_t n_low = blk_pred_pass(CB, nullptr, P, W, sh, warp, lane,
+                                       [&](int p) { return ldq(p) < thr.q_lora; });
+  uint32_t rc_n, rc_status;
+  if (n_low > 0) {
+    // default (adapter active in none of the low-queue pods): "can accept LoRA Adapter" on the
+    // low-queue set, falling back to that set, then queueAndKVCacheFilter   scheduler.go:65-69,49-56
+    uint32_t nc = 0;
+    for (int w = warp; w < W; w += kWarpsPerCta) {
+      const uint32_t t = CB[w] & M_room[w];
+      if (lane == 0) TMP[w] = t;
+      nc += __popc(t);
+    }
+    nc = blk_sum(nc, sh, warp, lane);
+    if (nc == 0) {
+      for (int w = threadIdx.x; w < W; w += kCtaThreads) TMP[w] = CB[w];
+      nc = n_low;
+    }
+    __syncthreads();
+    nc = blk_least_queuing<kStaged>(f, TMP, W, nc, sh, warp, lane);
+    rc_n = blk_least_kv<kStaged>(f, TMP, W, nc, sh, warp, lane);
+    rc_status = rc_n ? LIG_OK : LIG_EMPTY;
+    if (blockIdx.x == 0 && warp == 0 && rc_n) compact_mask_to_list(TMP, W, lane, lists + rc_row);
+    __syncthreads();
+  } else {
+    // low-queue filter failed: all pods -> least queuing -> low cost LoRA -> least KV  scheduler.go:71,35-46
+    uint32_t ny = blk_pred_pass(TMP, nullptr, P, W, sh, warp, lane, [&](int) { return true; });
+    ny = blk_least_queuing<kStaged>(f, TMP, W, ny, sh, warp, lane);
+    uint32_t nz = 0;
+    for (int w = warp; w < W; w += kWarpsPerCta) {
+      const uint32_t y = TMP[w], r = M_room[w];
+      if (lane == 0) { CZ[w] = y & r; CB[w] = y & ~r; }
+      nz += __popc(y & r);
+    }
+    nz = blk_sum(nz, sh, warp, lane);
+    if (nz > 0) {
+      for (int w = threadIdx.x; w < W; w += kCtaThreads) TMP[w] = CZ[w];
+      ny = nz;
+    }
+    __syncthreads();
+    rc_n = blk_least_kv<kStaged>(f, TMP, W, ny, sh, warp, lane);
+    rc_status = rc_n ? LIG_OK : LIG_EMPTY;
+    if (blockIdx.x == 0 && warp == 0 && rc_n) compact_mask_to_list(TMP, W, lane, lists + rc_row);
     __syncthreads();
   }
-  const int n_classes = 2 * (s.A + 1);
+  // sheddable side: "has capacity for sheddable requests"                 scheduler.go:74-79
+  uint32_t rs_n = 0, rs_status = LIG_DROP;
+  const uint32_t n_shed = blk_pred_pass(TMP, nullptr, P, W, sh, warp, lane, [&](int p) {
+    return ldq(p) <= thr.q_crit && ld_kv<kStaged>(f, p) <= thr.kv_thr;
+  });
+  if (n_shed > 0) {
+    uint32_t ny = blk_least_queuing<kStaged>(f, TMP, W, n_shed, sh, warp, lane);
+    uint32_t nz = 0;
+    for (int w = warp; w < W; w += kWarpsPerCta) {
+      const uint32_t y = TMP[w], r = M_room[w];
+      if (lane == 0) { SZ[w] = y & r; SB[w] = y & ~r; }
+      nz += __popc(y & r);
+    }
+    nz = blk_sum(nz, sh, warp, lane);
+    if (nz > 0) {
+      for (int w = threadIdx.x; w < W; w += kCtaThreads) TMP[w] = SZ[w];
+      ny = nz;
+    }
+    __syncthreads();
+    rs_n = blk_least_kv<kStaged>(f, TMP, W, ny, sh, warp, lane);
+    rs_status = rs_n ? LIG_OK : LIG_EMPTY;
+    if (blockIdx.x == 0 && warp == 0 && rs_n) compact_mask_to_list(TMP, W, lane, lists + rs_row);
+  }
+  __syncthreads();
+
+  // ---- per class (one warp each): AND the adapter row with the shared mask --------------------
   for (int c = blockIdx.x * kWarpsPerCta + warp; c < n_classes; c += gridDim.x * kWarpsPerCta) {
-    const bool critical = c >= s.A + 1;
-    const int a = critical ? c - (s.A + 1) : c;
-    const uint32_t* Hrow = stage_adapter_row(s, a, H, lane);
-    EvalResult r = tree_eval_warp<kStaged>(f, Hrow, critical, thr, s.P, s.W, X, T, lane);
-    uint16_t* list = lists + (size_t)c * list_stride;
-    uint32_t base = 0;
-    if (r.n > 0) {
-      for (int w = 0; w < s.W; ++w) {
-        uint32_t word = r.mask[w];
-        if (word == 0) continue;
-        if ((word >> lane) & 1u) {
-          list[base + __popc(word & ((1u << lane) - 1u))] = (uint16_t)(w * 32 + lane);
+    const bool critical = c >= A + 1;
+    const int a = critical ? c - (A + 1) : c;
+    const uint32_t* row = a < A ? s.bitmap + (size_t)a * W : nullptr;
+    ClassEntry e;
+    if (!critical && n_shed == 0) {
+      e = make_entry(0u, (uint32_t)LIG_DROP, kRowOwn);                     // scheduler.go:83-89
+    } else {
+      const uint32_t* Bm = critical ? CB : SB;
+      const uint32_t* Zm = critical ? (n_low > 0 ? nullptr : CZ) : SZ;
+      uint32_t hit = 0;
+      if (row) {
+        for (int w = lane; w < W; w += 32) {
+          const uint32_t t = Bm[w] & __ldg(row + w);
+          X[w] = t;
+          hit += __popc(t);
         }
-        base += __popc(word);
+        hit = __reduce_add_sync(kFull, hit);
+      }
+      if (hit == 0) {
+        e = critical ? make_entry(rc_n, rc_status, kRowCriticalDefault)
+                     : make_entry(rs_n, rs_status, kRowSheddableDefault);
+      } else {
+        uint32_t n = hit;
+        if (Zm) {   // low cost LoRA: (affinity | room) on the least-queuing set     filter.go:163-166
+          n = 0;
+          for (int w = lane; w < W; w += 32) {
+            const uint32_t t = X[w] | Zm[w];
+            X[w] = t;
+            n += __popc(t);
+          }
+          n = __reduce_add_sync(kFull, n);
+        }
+        __syncwarp();
+        if (critical && n_low > 0)      // "affinity LoRA" succeeded -> queueAndKVCacheFilter
+          n = sparse_least_queuing<kStaged>(f, X, W, lane, n);
+        n = sparse_least_kv<kStaged>(f, X, W, lane, n);
+        const uint32_t off = (uint32_t)c * (uint32_t)list_stride;
+        if (n) compact_mask_to_list(X, W, lane, lists + off);
+        e = make_entry(n, n ? (uint32_t)LIG_OK : (uint32_t)LIG_EMPTY, kRowOwn);
       }
     }
-    if (lane == 0) {
-      ClassEntry e;
-      e.n_status = r.n | (r.status << 16);
-      e.max_accept = r.n ? max_accept_for(r.n) : 0u;
-      cls[c] = e;
-    }
+    if (lane == 0) cls[c] = e;
     __syncwarp();
   }
 }
@@ -388,36 +789,65 @@ lig_class_build_kernel(SnapView s, Thr thr, ClassEntry* __restrict__ cls,
 // contiguous bytes and every store 256.  All loads of a thread are issued before the first use.
 constexpr int kPickThreads = 256;
 
+__device__ __forceinline__ int2 pick_one(const int4 r, const uint2* __restrict__ cls,
+                                         const uint16_t* __restrict__ lists, uint32_t list_stride,
+                                         uint32_t A, uint64_t seed) {
+  const uint32_t critical = (uint32_t)r.y & LIG_REQ_CRITICAL;
+  const uint64_t key = ((uint64_t)(uint32_t)r.w << 32) | (uint32_t)r.z;
+  const uint32_t a = min((uint32_t)r.x, A);          // ids outside [0, A) (negative too) -> A
+  const uint32_t c = critical * (A + 1u) + a;
+  const uint2 e = __ldg(cls + c);                    // {info, magic}
+  int pod = -1;
+  if (e.x >> 16) {
+    const uint32_t k = int31n_magic(seed ^ key, e.x, e.y);
+    const uint32_t row = class_list_row(e.x, c, 2u * (A + 1u));
+    pod = (int)__ldg(lists + (row * list_stride + k));
+  }
+  return make_int2(pod, (int)(e.x & 0xffff0003u));   // {pod_idx, status | n_survivors << 16}
+}
+
+// 8 CTAs/SM (<= 32 registers) so a 2^20-request batch (1024 CTAs) is a single wave on 148 SMs.
 template <int kPerThread>
-__global__ void __launch_bounds__(kPickThreads)
+__global__ void __launch_bounds__(kPickThreads, kPerThread <= 4 ? 8 : 4)
 lig_pick_stream_kernel(const int4* __restrict__ reqs, int2* __restrict__ out, int R,
                        const uint2* __restrict__ cls, const uint16_t* __restrict__ lists,
-                       int list_stride, int A, uint64_t seed) {
-  const int base = blockIdx.x * (kPickThreads * kPerThread) + threadIdx.x;
-  int4 r[kPerThread];
-#pragma unroll
-  for (int j = 0; j < kPerThread; ++j) {
-    int i = base + j * kPickThreads;
-    if (i < R) r[j] = ld_stream_int4(reqs + i);
-  }
-#pragma unroll
-  for (int j = 0; j < kPerThread; ++j) {
-    int i = base + j * kPickThreads;
-    if (i >= R) continue;
-    const int adapter = r[j].x;
-    const uint32_t critical = (uint32_t)r[j].y & LIG_REQ_CRITICAL;
-    const uint64_t key = ((uint64_t)(uint32_t)r[j].w << 32) | (uint32_t)r[j].z;
-    const int a = ((unsigned)adapter < (unsigned)A) ? adapter : A;
-    const int c = (int)critical * (A + 1) + a;
-    const uint2 e = __ldg(cls + c);
-    const uint32_t n = e.x & 0xffffu;
-    int pod = -1;
+                       int list_stride, int A, uint64_t seed, const int4* __restrict__ prefetch) {
+  constexpr int kPerCta = kPickThreads * kPerThread;
+  const int first = blockIdx.x * kPerCta;
+  // Cross-kernel software pipeline: while this batch is being scheduled, pull the CTA's slice of
+  // a LATER batch of the same queue from HBM into the 126 MB L2 with one TMA-family bulk
+  // prefetch (every descriptor still crosses HBM exactly once; it just does so while this
+  // kernel is busy with its class lookups and stores, so HBM never idles at kernel boundaries).
+  if (prefetch != nullptr && threadIdx.x == 0) {
+    const int n = min(kPerCta, R - first);
     if (n > 0) {
-      uint32_t k = int31n(seed ^ key, n, e.y);
-      pod = (int)__ldg(lists + (size_t)((uint32_t)c * (uint32_t)list_stride + k));
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;"
+                   :: "l"(prefetch + first), "r"(n * 16) : "memory");
     }
-    // lig_pick {int32 pod_idx; uint16 status; uint16 n_survivors}
-    st_stream_int2(out + i, make_int2(pod, (int)((e.x >> 16) | (n << 16))));
+  }
+  // Batches of one queue are independent: let the next batch's grid (launched with programmatic
+  // stream serialization, see launch_pick) start as soon as SM slots free up.  A no-op for a
+  // normally launched successor.
+  asm volatile("griddepcontrol.launch_dependents;");
+  const int4* src = reqs + first + threadIdx.x;
+  int2* dst = out + first + threadIdx.x;
+  int4 r[kPerThread];
+  if (first + kPerCta <= R) {              // full CTA: no per-request bounds checks
+#pragma unroll
+    for (int j = 0; j < kPerThread; ++j) r[j] = ld_stream_int4(src + j * kPickThreads);
+#pragma unroll
+    for (int j = 0; j < kPerThread; ++j)
+      st_stream_int2(dst + j * kPickThreads,
+                     pick_one(r[j], cls, lists, (uint32_t)list_stride, (uint32_t)A, seed));
+  } else {                                 // ragged tail CTA
+#pragma unroll
+    for (int j = 0; j < kPerThread; ++j) {
+      const int i = first + threadIdx.x + j * kPickThreads;
+      if (i < R)
+        st_stream_int2(dst + j * kPickThreads,
+                       pick_one(ld_stream_int4(src + j * kPickThreads), cls, lists,
+                                (uint32_t)list_stride, (uint32_t)A, seed));
+    }
   }
 }
 
