@@ -36,6 +36,12 @@ L2_BYTES = 126 * 1024 * 1024
 FALLBACK_HBM_GBS = 6650.0     # /opt/skills/guides/B200_PROFILING.md fallback
 
 
+def workload_label(name, R, P, A):
+    idx = {"C2": 1, "C3": 2, "C4": 3, "C5": 4}[name]
+    return (f"{name}: R={R} requests/GPU/step x P={P} pods, A={A} adapters "
+            f"(BASELINE.json configs[{idx}])")
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -54,6 +60,8 @@ def parse_args():
     ap.add_argument("--timed-only", action="store_true",
                     help="run only warm-up + the K-step timed region (for ncu launch lists)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-streaming", action="store_true",
+                    help="skip the C5 streaming leg (100K req/s Poisson, p50/p99 decision latency)")
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="target CPU time of the baseline sample")
     return ap.parse_args()
 
@@ -148,6 +156,42 @@ def cpu_reference_rate(snap, reqs, seed, nthreads, seconds):
     return sample / dt, sample
 
 
+def streaming_leg(device, rate=1e5, seconds=3.0, threads=32, window_us=5):
+    """BASELINE.json configs[4]: sustained 100K req/s Poisson into a 256-pod pool through the native
+    C++ host runtime (concurrent blocking Schedule callers -> micro-batches -> one C-ABI call per
+    flush, snapshot re-packed every 50 ms); latency = completion - scheduled arrival."""
+    from llm_instance_gateway_b200 import host as H
+    from llm_instance_gateway_b200.backend import Metrics, Pod, PodMetrics
+    c = WL.CONFIGS["C5"]
+    snap = WL.make_snapshot(c["P"], c["A"])
+    p = snap.packed
+    pods = [PodMetrics(Pod(f"pod-{i}", f"address-{i}"),
+                       Metrics(WaitingQueueSize=int(snap.q64[i]), KVCacheUsagePercent=float(p.kv[i]),
+                               MaxActiveModels=int(snap.max_active64[i]),
+                               ActiveModels={WL.adapter_name(a): 1 for a in snap.active[i]}))
+            for i in range(p.P)]
+    prov = H.HostProvider(pods)
+    sched = H.HostScheduler(prov, device=device, max_pods=c["P"], max_adapters=c["A"], max_batch=1 << 14,
+                            flush_size=4096, batch_window_us=window_us, refresh_interval_ms=50)
+    models = [WL.adapter_name(a) for a in range(c["A"])] + [WL.UNKNOWN_MODEL]
+    models = models + models
+    critical = [False] * (c["A"] + 1) + [True] * (c["A"] + 1)
+    try:
+        lat, nerr = sched.stream_bench(rate, seconds, threads, models, critical, seed=5)
+        st = sched.stats()
+    finally:
+        sched.close()
+        prov.close()
+    return {"workload": f"C5: {rate:.0f} req/s Poisson for {seconds:.0f} s into P={c['P']} pods, A={c['A']} adapters",
+            "achieved_req_per_s": len(lat) / seconds, "latency_us": {
+                "p50": float(np.percentile(lat, 50)), "p90": float(np.percentile(lat, 90)),
+                "p99": float(np.percentile(lat, 99)), "p99.9": float(np.percentile(lat, 99.9)),
+                "max": float(lat.max())},
+            "errors": int(nerr), "caller_threads": threads, "batch_window_us": window_us,
+            "batches": st["batches"], "avg_batch": st["scheduled"] / max(st["batches"], 1),
+            "snapshot_refreshes": st["refreshes"]}
+
+
 def run_reference(args, cfg, R):
     """--impl reference: the reference's CPU algorithm (oracle port; the Go original cannot be
     built in this image) on the host cores, each step a bounded sample of the workload."""
@@ -180,7 +224,8 @@ def run_reference(args, cfg, R):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64+f64",
         "data": "synthetic",
-        "config": {"workload": f"{args.workload}: R={R} requests/GPU x P={cfg['P']} pods, A={cfg['A']} adapters",
+        "config": {"workload": workload_label(args.workload, R, cfg["P"], cfg["A"]),
+                   "requests_per_gpu": R, "pods": cfg["P"], "adapters": cfg["A"],
                    "note": "C restatement of the Go scheduler (Go toolchain absent): same tree, pointer "
                            "slices, string-keyed ActiveModels maps, fresh slice per stage; all host threads"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": nthreads, "kind": "port", "sample": sample},
@@ -380,8 +425,7 @@ def main():
             "ms_per_step": ms_region / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "int32/u64 index arithmetic + f64 compares", "data": "synthetic",
             "config": {
-                "workload": f"{args.workload}: R={R} requests/GPU/step x P={P} pods, A={A} adapters "
-                            f"(BASELINE.json configs[{ {'C2': 1, 'C3': 2, 'C4': 3, 'C5': 4}[args.workload] }])",
+                "workload": workload_label(args.workload, R, P, A),
                 "requests_per_gpu": R, "pods": P, "adapters": A, "parallelism": f"request-sharded x{world}",
                 "l2": f"{nb} distinct resident batches ({nb * R * 24 / 2**20:.0f} MiB in+out) cycled: "
                       "inputs larger than the 126 MB L2",
@@ -406,6 +450,8 @@ def main():
                             "requests": Rs, "note": "lig_scan_kernel: per-request tree walk, no class tables"},
             "parity_checked": parity_n,
         }
+        if world == 1 and not args.no_streaming:
+            line["streaming"] = streaming_leg(local_rank)
         if world == 1 and not args.no_cpu_baseline:
             from oracle import binding as oracle
             nthreads = oracle.hardware_threads()
