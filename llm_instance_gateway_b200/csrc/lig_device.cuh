@@ -175,6 +175,7 @@ __device__ __forceinline__ uint32_t stage_least_queuing(const Fields& f, uint32_
       keep = v >= (long long)mn && v <= thr;                                 // filter.go:117
     }
     uint32_t nw = __ballot_sync(kFull, keep);
+    __syncwarp();  // every lane's read of X[w] is ordered before lane 0 overwrites it
     if (lane == 0) X[w] = nw;
     cnt += __popc(nw);
   }
@@ -217,6 +218,7 @@ __device__ __forceinline__ uint32_t stage_least_kv(const Fields& f, uint32_t* X,
       keep = v >= mn && v <= thr;
     }
     uint32_t nw = __ballot_sync(kFull, keep);
+    __syncwarp();  // every lane's read of X[w] is ordered before lane 0 overwrites it
     if (lane == 0) X[w] = nw;
     cnt += __popc(nw);
   }
@@ -454,6 +456,7 @@ __device__ __forceinline__ uint32_t blk_least_queuing(const Fields& f, uint32_t*
       keep = v >= (long long)mn && v <= thr;
     }
     const uint32_t nw = __ballot_sync(kFull, keep);
+    __syncwarp();  // every lane's read of X[w] is ordered before lane 0 overwrites it
     if (lane == 0) X[w] = nw;
     cnt += __popc(nw);
   }
@@ -499,6 +502,7 @@ __device__ __forceinline__ uint32_t blk_least_kv(const Fields& f, uint32_t* X, i
       keep = v >= mn && v <= thr;
     }
     const uint32_t nw = __ballot_sync(kFull, keep);
+    __syncwarp();  // every lane's read of X[w] is ordered before lane 0 overwrites it
     if (lane == 0) X[w] = nw;
     cnt += __popc(nw);
   }
