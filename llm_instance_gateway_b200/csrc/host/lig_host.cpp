@@ -63,6 +63,7 @@ Scheduler::~Scheduler() {
   {
     std::lock_guard<std::mutex> lk(mu_);
     stop_ = true;
+    stop_flag_.store(true);
   }
   cv_.notify_all();
   if (batcher_.joinable()) batcher_.join();
@@ -135,8 +136,17 @@ Status Scheduler::Schedule(const LLMRequest& req, backend::Pod* targetPod) {
     if (stop_) return Errorf(Internal, "scheduler is shut down");
     if (pending_.empty()) oldest_ = std::chrono::steady_clock::now();
     pending_.push_back(&w);
+    pending_count_.store((int)pending_.size(), std::memory_order_release);
   }
-  cv_.notify_all();
+  if (!opt_.busy_poll) cv_.notify_all();
+  if (opt_.caller_spin.count() > 0) {
+    const auto until = std::chrono::steady_clock::now() + opt_.caller_spin;
+    while (w.done.load(std::memory_order_acquire) == 0 && std::chrono::steady_clock::now() < until) {
+#if defined(__x86_64__)
+      __builtin_ia32_pause();
+#endif
+    }
+  }
   w.done.wait(0, std::memory_order_acquire);
   if (w.status.ok() && targetPod) *targetPod = std::move(w.pod);
   return w.status;
@@ -146,12 +156,36 @@ void Scheduler::BatcherLoop() {
   std::vector<Waiter*> batch;
   std::unique_lock<std::mutex> lk(mu_);
   for (;;) {
-    cv_.wait(lk, [&] { return stop_ || !pending_.empty(); });
-    if (pending_.empty() && stop_) break;
-    const auto deadline = oldest_ + opt_.batch_window;
-    cv_.wait_until(lk, deadline, [&] { return stop_ || (int)pending_.size() >= opt_.flush_size; });
+    if (opt_.busy_poll) {
+      lk.unlock();
+      while (pending_count_.load(std::memory_order_acquire) == 0) {
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+        if (stop_flag_.load(std::memory_order_relaxed)) break;
+      }
+      lk.lock();
+      if (pending_.empty()) {
+        if (stop_) break;
+        continue;
+      }
+      const auto deadline = oldest_ + opt_.batch_window;
+      while ((int)pending_.size() < opt_.flush_size && std::chrono::steady_clock::now() < deadline && !stop_) {
+        lk.unlock();
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+        lk.lock();
+      }
+    } else {
+      cv_.wait(lk, [&] { return stop_ || !pending_.empty(); });
+      if (pending_.empty() && stop_) break;
+      const auto deadline = oldest_ + opt_.batch_window;
+      cv_.wait_until(lk, deadline, [&] { return stop_ || (int)pending_.size() >= opt_.flush_size; });
+    }
     batch.clear();
     batch.swap(pending_);
+    pending_count_.store(0, std::memory_order_release);
     lk.unlock();
     Flush(batch);
     lk.lock();

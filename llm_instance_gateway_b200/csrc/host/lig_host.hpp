@@ -92,6 +92,10 @@ struct Options {
   uint64_t seed = 0;                 // 0 = seed from std::random_device (Go's auto-seeded source)
   // >0: a refresher thread re-packs the provider's snapshot at this period.
   std::chrono::milliseconds refresh_interval{0};
+  // Latency knobs: the batcher thread polls its queue instead of sleeping on a condition
+  // variable, and callers spin this long on their result before blocking in the kernel.
+  bool busy_poll = false;
+  std::chrono::microseconds caller_spin{0};
   double kv_cache_threshold = 0.8;   // scheduler.go:15-24
   int64_t queue_threshold_critical = 5;
   int64_t queueing_threshold_lora = 50;
@@ -161,8 +165,10 @@ class Scheduler {
   std::mutex mu_;
   std::condition_variable cv_;
   std::vector<Waiter*> pending_;
+  std::atomic<int> pending_count_{0};
   std::chrono::steady_clock::time_point oldest_;
   bool stop_ = false;
+  std::atomic<bool> stop_flag_{false};
   std::thread batcher_, refresher_;
 
   mutable std::mutex stats_mu_;

@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 #include "lig_device.cuh"
 
@@ -256,10 +257,42 @@ int check_shape(const lig_ctx* c, int P, int A) {
   return 0;
 }
 
+// Ranges handed out by lig_host_alloc (and the ctx's own staging buffers): known to be pinned and
+// device-mapped, so the per-call driver query below can be skipped for them.
+struct PinnedRange { const char* base; size_t bytes; char* dev; };
+std::mutex g_pinned_mu;
+std::vector<PinnedRange> g_pinned;
+
+void register_pinned(void* host, size_t bytes) {
+  void* dev = nullptr;
+  if (cudaHostGetDevicePointer(&dev, host, 0) != cudaSuccess) {
+    cudaGetLastError();
+    return;
+  }
+  std::lock_guard<std::mutex> lk(g_pinned_mu);
+  g_pinned.push_back(PinnedRange{static_cast<const char*>(host), bytes, static_cast<char*>(dev)});
+}
+
+void unregister_pinned(void* host) {
+  std::lock_guard<std::mutex> lk(g_pinned_mu);
+  for (size_t i = 0; i < g_pinned.size(); ++i)
+    if (g_pinned[i].base == host) {
+      g_pinned.erase(g_pinned.begin() + (long)i);
+      return;
+    }
+}
+
 // Device-visible alias of a page-locked host pointer (identical under UVA), or nullptr when p is
 // ordinary pageable memory.
 template <typename T>
 T* mapped_device_pointer(T* p) {
+  {
+    const char* q = reinterpret_cast<const char*>(p);
+    std::lock_guard<std::mutex> lk(g_pinned_mu);
+    for (const PinnedRange& r : g_pinned)
+      if (q >= r.base && q < r.base + r.bytes)
+        return reinterpret_cast<T*>(r.dev + (q - r.base));
+  }
   cudaPointerAttributes at;
   if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
     cudaGetLastError();
@@ -389,6 +422,8 @@ static int create_impl(lig_ctx* c, int device, int max_pods, int max_adapters, i
   CUDA_TRY(cudaMalloc(&c->d_out, (size_t)max_batch * sizeof(lig_pick)));
   CUDA_TRY(cudaHostAlloc(&c->h_reqs, (size_t)max_batch * sizeof(lig_req), cudaHostAllocMapped));
   CUDA_TRY(cudaHostAlloc(&c->h_out, (size_t)max_batch * sizeof(lig_pick), cudaHostAllocMapped));
+  register_pinned(c->h_reqs, (size_t)max_batch * sizeof(lig_req));
+  register_pinned(c->h_out, (size_t)max_batch * sizeof(lig_pick));
   return 0;
 }
 
@@ -442,6 +477,8 @@ void lig_destroy(lig_ctx* c) {
   cudaFree(c->d_reqs);
   cudaFree(c->d_out);
   cudaFree(c->d_masks);
+  if (c->h_reqs) unregister_pinned(c->h_reqs);
+  if (c->h_out) unregister_pinned(c->h_out);
   cudaFreeHost(c->h_reqs);
   cudaFreeHost(c->h_out);
   delete c;
@@ -694,11 +731,14 @@ void* lig_host_alloc(size_t bytes) {
     fail(LIG_ERR_CUDA, "cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
     return nullptr;
   }
+  register_pinned(p, bytes);
   return p;
 }
 
 void lig_host_free(void* p) {
-  if (p) cudaFreeHost(p);
+  if (!p) return;
+  unregister_pinned(p);
+  cudaFreeHost(p);
 }
 
 uint64_t lig_kernel_launches(const lig_ctx* c) { return c ? c->launches.load() : 0; }

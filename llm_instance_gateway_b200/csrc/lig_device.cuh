@@ -384,7 +384,7 @@ __device__ __forceinline__ const uint32_t* stage_adapter_row(const SnapView& s, 
 // row with a shared mask; only classes whose adapter actually intersects the mask run their own
 // range filters, on the (sparse) set bits.  Classes that do not intersect share one of two
 // default survivor lists.  lig_scan_kernel keeps the plain per-request walk (tree_eval_warp), so
-// the GPU holds two independent formulations of the tree, both checked against the oracle.
+// the GPU holds two independent formulations of the tree (the parity tests check both).
 
 struct BuildShared {        // block-wide scalars of the shared stages (shared memory)
   uint32_t n_shed;          // |S|, S = {q <= q_crit && kv <= kv_thr}              scheduler.go:74-79
