@@ -156,7 +156,7 @@ def cpu_reference_rate(snap, reqs, seed, nthreads, seconds):
     return sample / dt, sample
 
 
-def streaming_leg(device, rate=1e5, seconds=3.0, threads=32, window_us=5):
+def streaming_leg(device, rate=1e5, seconds=3.0, threads=32, window_us=2):
     """BASELINE.json configs[4]: sustained 100K req/s Poisson into a 256-pod pool through the native
     C++ host runtime (concurrent blocking Schedule callers -> micro-batches -> one C-ABI call per
     flush, snapshot re-packed every 50 ms); latency = completion - scheduled arrival."""
@@ -172,7 +172,8 @@ def streaming_leg(device, rate=1e5, seconds=3.0, threads=32, window_us=5):
             for i in range(p.P)]
     prov = H.HostProvider(pods)
     sched = H.HostScheduler(prov, device=device, max_pods=c["P"], max_adapters=c["A"], max_batch=1 << 14,
-                            flush_size=4096, batch_window_us=window_us, refresh_interval_ms=50)
+                            flush_size=4096, batch_window_us=window_us, refresh_interval_ms=50,
+                            busy_poll=True, caller_spin_us=100)
     models = [WL.adapter_name(a) for a in range(c["A"])] + [WL.UNKNOWN_MODEL]
     models = models + models
     critical = [False] * (c["A"] + 1) + [True] * (c["A"] + 1)
@@ -188,6 +189,7 @@ def streaming_leg(device, rate=1e5, seconds=3.0, threads=32, window_us=5):
                 "p99": float(np.percentile(lat, 99)), "p99.9": float(np.percentile(lat, 99.9)),
                 "max": float(lat.max())},
             "errors": int(nerr), "caller_threads": threads, "batch_window_us": window_us,
+            "batcher": "busy-polling thread, callers spin 100 us before blocking",
             "batches": st["batches"], "avg_batch": st["scheduled"] / max(st["batches"], 1),
             "snapshot_refreshes": st["refreshes"]}
 
