@@ -30,6 +30,16 @@ int fail(int code, const char* fmt, ...) {
   return code;
 }
 
+#define CUDA_TRY_RC(expr)                                                                   \
+  do {                                                                                      \
+    cudaError_t e__ = (expr);                                                               \
+    if (e__ != cudaSuccess) {                                                               \
+      *rc = fail(LIG_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__),     \
+                 __FILE__, __LINE__);                                                       \
+      return nullptr;                                                                       \
+    }                                                                                       \
+  } while (0)
+
 #define CUDA_TRY(expr)                                                                      \
   do {                                                                                      \
     cudaError_t e__ = (expr);                                                               \
@@ -77,6 +87,20 @@ constexpr int kChunk = 1 << 16;  // requests per chunk of the host-buffer pipeli
 
 }  // namespace
 
+namespace {
+struct QueueGraph {
+  int slot_index = 0, P = 0, A = 0, R = 0, ns = 0, pd = 0, ppt = 0;
+  std::vector<const lig_req*> reqs;
+  std::vector<lig_pick*> outs;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  cudaGraphNode_t seed_node = nullptr;
+  uint64_t* d_seed = nullptr;
+  uint64_t last_use = 0;
+};
+constexpr size_t kMaxQueueGraphs = 24;
+}  // namespace
+
 struct lig_ctx {
   int device = 0;
   int max_pods = 0, max_adapters = 0, max_batch = 0;
@@ -102,6 +126,22 @@ struct lig_ctx {
   int prefetch_distance = 1;  // env LIG_PREFETCH=d (0 = off): batch b pulls batch b+d of the same queue into L2
   cudaEvent_t fork = nullptr;
   cudaEvent_t join[kPipeStreams] = {};
+  // cached CUDA graphs of batch queues (env LIG_GRAPH=0 disables): a queue with the same
+  // buffers, shape and snapshot slot is replayed with one cudaGraphLaunch instead of one
+  // cudaLaunchKernel per batch
+  bool use_graph = true;
+  int graph_min_batches = 4;
+  // queues of small batches (R <= merge_max_requests, env LIG_MERGE_MAX) run as ONE launch with
+  // blockIdx.y = batch; the item table goes through a small pinned ring
+  int merge_max_requests = 1 << 17;
+  static constexpr int kItemSlots = 4;
+  static constexpr int kMaxItems = 65535;
+  QueueItem* d_items[kItemSlots] = {};
+  QueueItem* h_items[kItemSlots] = {};
+  cudaEvent_t items_free[kItemSlots] = {};
+  int item_slot = 0;
+  std::vector<struct QueueGraph*> graphs;
+  uint64_t graph_clock = 0;
 };
 
 namespace {
@@ -176,6 +216,7 @@ template <int kPerThread>
 cudaError_t launch_pick_variant(int grid, cudaStream_t stream, bool overlap_prev, const int4* in,
                                 int2* out, int R, const uint2* cls, const uint16_t* lists,
                                 int stride, int A, uint64_t seed, const int4* prefetch) {
+  const uint64_t* no_cell = nullptr;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(kPickThreads);
@@ -187,7 +228,7 @@ cudaError_t launch_pick_variant(int grid, cudaStream_t stream, bool overlap_prev
   cfg.attrs = attr;
   cfg.numAttrs = overlap_prev ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, lig_pick_stream_kernel<kPerThread>, in, out, R, cls, lists, stride, A,
-                            seed, prefetch);
+                            seed, prefetch, no_cell);
 }
 
 // overlap_prev: the previous operation on `stream` is a pick kernel of the same queue call, whose
@@ -255,6 +296,107 @@ int check_shape(const lig_ctx* c, int P, int A) {
   if (A < 0 || A > c->max_adapters)
     return fail(LIG_ERR_INVALID, "A=%d outside [0, max_adapters=%d]", A, c->max_adapters);
   return 0;
+}
+
+void destroy_queue_graph(QueueGraph* g) {
+  if (!g) return;
+  if (g->exec) cudaGraphExecDestroy(g->exec);
+  if (g->graph) cudaGraphDestroy(g->graph);
+  if (g->d_seed) cudaFree(g->d_seed);
+  delete g;
+}
+
+template <int kPerThread>
+void* pick_kernel_ptr() { return reinterpret_cast<void*>(&lig_pick_stream_kernel<kPerThread>); }
+
+// Build the graph of one queue: a root node that publishes the seed, then the batches as
+// kernel nodes in `ns` independent chains (batch b after batch b - ns), mirroring the forked
+// streams of the ungraphed path; batch b prefetches batch b + pd.
+int build_queue_graph(const Slot& s, QueueGraph* g, int n_batches) {
+  CUDA_TRY(cudaMalloc(&g->d_seed, sizeof(uint64_t)));
+  CUDA_TRY(cudaGraphCreate(&g->graph, 0));
+  uint64_t seed0 = 0;
+  void* seed_args[2] = {&g->d_seed, &seed0};
+  cudaKernelNodeParams kp = {};
+  kp.func = reinterpret_cast<void*>(&lig_set_seed_kernel);
+  kp.gridDim = dim3(1);
+  kp.blockDim = dim3(1);
+  kp.kernelParams = seed_args;
+  CUDA_TRY(cudaGraphAddKernelNode(&g->seed_node, g->graph, nullptr, 0, &kp));
+  void* fn;
+  switch (g->ppt) {
+    case 1: fn = pick_kernel_ptr<1>(); break;
+    case 2: fn = pick_kernel_ptr<2>(); break;
+    case 8: fn = pick_kernel_ptr<8>(); break;
+    default: fn = pick_kernel_ptr<4>(); break;
+  }
+  const uint2* cls = reinterpret_cast<const uint2*>(s.d_cls);
+  const uint16_t* lists = s.d_lists;
+  int stride = s.P > 0 ? s.P : 1;
+  int A = s.A, R = g->R;
+  const int per_cta = kPickThreads * g->ppt;
+  std::vector<cudaGraphNode_t> nodes((size_t)n_batches);
+  for (int b = 0; b < n_batches; ++b) {
+    const int4* in = reinterpret_cast<const int4*>(g->reqs[(size_t)b]);
+    int2* out = reinterpret_cast<int2*>(g->outs[(size_t)b]);
+    uint64_t offset = (uint64_t)b;
+    const int4* pf = (g->pd > 0 && b + g->pd < n_batches)
+                         ? reinterpret_cast<const int4*>(g->reqs[(size_t)(b + g->pd)]) : nullptr;
+    const uint64_t* cell = g->d_seed;
+    void* args[11] = {&in, &out, &R, &cls, &lists, &stride, &A, &offset, &pf, &cell, nullptr};
+    cudaKernelNodeParams np = {};
+    np.func = fn;
+    np.gridDim = dim3((unsigned)((R + per_cta - 1) / per_cta));
+    np.blockDim = dim3(kPickThreads);
+    np.kernelParams = args;
+    cudaGraphNode_t dep = b < g->ns ? g->seed_node : nodes[(size_t)(b - g->ns)];
+    CUDA_TRY(cudaGraphAddKernelNode(&nodes[(size_t)b], g->graph, &dep, 1, &np));
+  }
+  CUDA_TRY(cudaGraphInstantiate(&g->exec, g->graph, 0));
+  return 0;
+}
+
+// Find or build the cached graph of this queue; nullptr (and *rc = 0) when graphs do not apply.
+QueueGraph* queue_graph_for(lig_ctx* c, const Slot& s, const lig_req* const* d_reqs, int R,
+                            lig_pick* const* d_out, int n_batches, int ns, int pd, int* rc) {
+  *rc = 0;
+  if (!c->use_graph || n_batches < c->graph_min_batches || R == 0) return nullptr;
+  const int slot_index = (int)(&s - c->slot);
+  for (QueueGraph* g : c->graphs) {
+    if (g->slot_index != slot_index || g->P != s.P || g->A != s.A || g->R != R || g->ns != ns ||
+        g->pd != pd || g->ppt != c->pick_per_thread || (int)g->reqs.size() != n_batches)
+      continue;
+    if (memcmp(g->reqs.data(), d_reqs, (size_t)n_batches * sizeof(void*)) != 0 ||
+        memcmp(g->outs.data(), d_out, (size_t)n_batches * sizeof(void*)) != 0)
+      continue;
+    g->last_use = ++c->graph_clock;
+    return g;
+  }
+  if (c->graphs.size() >= kMaxQueueGraphs) {   // evict the least recently used
+    size_t victim = 0;
+    for (size_t i = 1; i < c->graphs.size(); ++i)
+      if (c->graphs[i]->last_use < c->graphs[victim]->last_use) victim = i;
+    CUDA_TRY_RC(cudaDeviceSynchronize());
+    destroy_queue_graph(c->graphs[victim]);
+    c->graphs.erase(c->graphs.begin() + (long)victim);
+  }
+  QueueGraph* g = new QueueGraph();
+  g->slot_index = slot_index;
+  g->P = s.P;
+  g->A = s.A;
+  g->R = R;
+  g->ns = ns;
+  g->pd = pd;
+  g->ppt = c->pick_per_thread;
+  g->reqs.assign(d_reqs, d_reqs + n_batches);
+  g->outs.assign(d_out, d_out + n_batches);
+  g->last_use = ++c->graph_clock;
+  if ((*rc = build_queue_graph(s, g, n_batches)) != 0) {
+    destroy_queue_graph(g);
+    return nullptr;
+  }
+  c->graphs.push_back(g);
+  return g;
 }
 
 // Ranges handed out by lig_host_alloc (and the ctx's own staging buffers): known to be pinned and
@@ -406,6 +548,13 @@ static int create_impl(lig_ctx* c, int device, int max_pods, int max_adapters, i
     if (v2 == 1 || v2 == 2 || v2 == 4 || v2 == 8) c->pick_per_thread = v2;
   }
   if (const char* e = getenv("LIG_PDL")) c->use_pdl = atoi(e) != 0;
+  if (const char* e = getenv("LIG_GRAPH")) c->use_graph = atoi(e) != 0;
+  if (const char* e = getenv("LIG_MERGE_MAX")) c->merge_max_requests = atoi(e);
+  for (int i = 0; i < lig_ctx::kItemSlots; ++i) {
+    CUDA_TRY(cudaMalloc(&c->d_items[i], sizeof(QueueItem) * lig_ctx::kMaxItems));
+    CUDA_TRY(cudaHostAlloc(&c->h_items[i], sizeof(QueueItem) * lig_ctx::kMaxItems, cudaHostAllocDefault));
+    CUDA_TRY(cudaEventCreateWithFlags(&c->items_free[i], cudaEventDisableTiming));
+  }
   if (const char* e = getenv("LIG_PREFETCH")) {
     int v2 = atoi(e);
     if (v2 >= 0 && v2 <= 16) c->prefetch_distance = v2;
@@ -468,6 +617,13 @@ void lig_destroy(lig_ctx* c) {
     if (s.ready) cudaEventDestroy(s.ready);
     if (s.idle) cudaEventDestroy(s.idle);
   }
+  for (int i = 0; i < lig_ctx::kItemSlots; ++i) {
+    cudaFree(c->d_items[i]);
+    cudaFreeHost(c->h_items[i]);
+    if (c->items_free[i]) cudaEventDestroy(c->items_free[i]);
+  }
+  for (QueueGraph* g : c->graphs) destroy_queue_graph(g);
+  c->graphs.clear();
   if (c->fork) cudaEventDestroy(c->fork);
   for (auto& ev : c->join)
     if (ev) cudaEventDestroy(ev);
@@ -590,6 +746,51 @@ int lig_schedule_batches_device(lig_ctx* c, uint64_t epoch, uint64_t seed,
   // while everything stays ordered with respect to `stream`.
   const int ns = (n_batches > 1) ? c->queue_streams : 1;
   const int pd = c->prefetch_distance;
+  if (n_batches >= 2 && R > 0 && R <= c->merge_max_requests) {
+    // small batches: one launch for up to 65535 of them
+    const uint2* cls = reinterpret_cast<const uint2*>(s->d_cls);
+    const int stride = s->P > 0 ? s->P : 1;
+    const int per_cta = kPickThreads * c->pick_per_thread;
+    for (int lo = 0; lo < n_batches; lo += lig_ctx::kMaxItems) {
+      const int n = (n_batches - lo) < lig_ctx::kMaxItems ? (n_batches - lo) : lig_ctx::kMaxItems;
+      const int slot = c->item_slot;
+      c->item_slot = (slot + 1) % lig_ctx::kItemSlots;
+      CUDA_TRY(cudaEventSynchronize(c->items_free[slot]));   // table of 4 queues ago has been copied
+      for (int b = 0; b < n; ++b)
+        c->h_items[slot][b] = QueueItem{reinterpret_cast<const int4*>(d_reqs[lo + b]),
+                                        reinterpret_cast<int2*>(d_out[lo + b]), seed + (uint64_t)(lo + b)};
+      CUDA_TRY(cudaMemcpyAsync(c->d_items[slot], c->h_items[slot], sizeof(QueueItem) * (size_t)n,
+                               cudaMemcpyHostToDevice, st));
+      CUDA_TRY(cudaEventRecord(c->items_free[slot], st));
+      const dim3 grid((unsigned)((R + per_cta - 1) / per_cta), (unsigned)n);
+      switch (c->pick_per_thread) {
+        case 1: lig_pick_queue_kernel<1><<<grid, kPickThreads, 0, st>>>(c->d_items[slot], R, cls, s->d_lists, stride, s->A); break;
+        case 2: lig_pick_queue_kernel<2><<<grid, kPickThreads, 0, st>>>(c->d_items[slot], R, cls, s->d_lists, stride, s->A); break;
+        case 8: lig_pick_queue_kernel<8><<<grid, kPickThreads, 0, st>>>(c->d_items[slot], R, cls, s->d_lists, stride, s->A); break;
+        default: lig_pick_queue_kernel<4><<<grid, kPickThreads, 0, st>>>(c->d_items[slot], R, cls, s->d_lists, stride, s->A); break;
+      }
+      CUDA_TRY(cudaGetLastError());
+      c->launches++;
+    }
+    CUDA_TRY(cudaEventRecord(s->idle, st));
+    return 0;
+  }
+  int grc = 0;
+  if (QueueGraph* g = queue_graph_for(c, *s, d_reqs, R, d_out, n_batches, ns, pd, &grc)) {
+    uint64_t seed_value = seed;
+    void* seed_args[2] = {&g->d_seed, &seed_value};
+    cudaKernelNodeParams kp = {};
+    kp.func = reinterpret_cast<void*>(&lig_set_seed_kernel);
+    kp.gridDim = dim3(1);
+    kp.blockDim = dim3(1);
+    kp.kernelParams = seed_args;
+    CUDA_TRY(cudaGraphExecKernelNodeSetParams(g->exec, g->seed_node, &kp));
+    CUDA_TRY(cudaGraphLaunch(g->exec, st));
+    c->launches += (uint64_t)n_batches + 1;
+    CUDA_TRY(cudaEventRecord(s->idle, st));
+    return 0;
+  }
+  if (grc != 0) return grc;
   if (ns == 1) {
     for (int b = 0; b < n_batches; ++b)
       if (int rc = launch_pick(c, *s, seed + (uint64_t)b, d_reqs[b], R, d_out[b], st, b > 0,

@@ -810,29 +810,14 @@ __device__ __forceinline__ int2 pick_one(const int4 r, const uint2* __restrict__
   return make_int2(pod, (int)(e.x & 0xffff0003u));   // {pod_idx, status | n_survivors << 16}
 }
 
-// 8 CTAs/SM (<= 32 registers) so a 2^20-request batch (1024 CTAs) is a single wave on 148 SMs.
+// One CTA's share of one batch: kPerThread requests per thread.
 template <int kPerThread>
-__global__ void __launch_bounds__(kPickThreads, kPerThread <= 4 ? 8 : 4)
-lig_pick_stream_kernel(const int4* __restrict__ reqs, int2* __restrict__ out, int R,
-                       const uint2* __restrict__ cls, const uint16_t* __restrict__ lists,
-                       int list_stride, int A, uint64_t seed, const int4* __restrict__ prefetch) {
+__device__ __forceinline__ void pick_cta(const int4* __restrict__ reqs, int2* __restrict__ out, int R,
+                                         int cta, const uint2* __restrict__ cls,
+                                         const uint16_t* __restrict__ lists, int list_stride, int A,
+                                         uint64_t seed) {
   constexpr int kPerCta = kPickThreads * kPerThread;
-  const int first = blockIdx.x * kPerCta;
-  // Cross-kernel software pipeline: while this batch is being scheduled, pull the CTA's slice of
-  // a LATER batch of the same queue from HBM into the 126 MB L2 with one TMA-family bulk
-  // prefetch (every descriptor still crosses HBM exactly once; it just does so while this
-  // kernel is busy with its class lookups and stores, so HBM never idles at kernel boundaries).
-  if (prefetch != nullptr && threadIdx.x == 0) {
-    const int n = min(kPerCta, R - first);
-    if (n > 0) {
-      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;"
-                   :: "l"(prefetch + first), "r"(n * 16) : "memory");
-    }
-  }
-  // Batches of one queue are independent: let the next batch's grid (launched with programmatic
-  // stream serialization, see launch_pick) start as soon as SM slots free up.  A no-op for a
-  // normally launched successor.
-  asm volatile("griddepcontrol.launch_dependents;");
+  const int first = cta * kPerCta;
   const int4* src = reqs + first + threadIdx.x;
   int2* dst = out + first + threadIdx.x;
   int4 r[kPerThread];
@@ -854,6 +839,59 @@ lig_pick_stream_kernel(const int4* __restrict__ reqs, int2* __restrict__ out, in
     }
   }
 }
+
+// 8 CTAs/SM (<= 32 registers) so a 2^20-request batch (1024 CTAs) is a single wave on 148 SMs.
+template <int kPerThread>
+__global__ void __launch_bounds__(kPickThreads, kPerThread <= 4 ? 8 : 4)
+lig_pick_stream_kernel(const int4* __restrict__ reqs, int2* __restrict__ out, int R,
+                       const uint2* __restrict__ cls, const uint16_t* __restrict__ lists,
+                       int list_stride, int A, uint64_t seed, const int4* __restrict__ prefetch,
+                       const uint64_t* __restrict__ seed_cell) {
+  constexpr int kPerCta = kPickThreads * kPerThread;
+  // Inside a replayed CUDA graph the per-call seed lives in device memory (written by the
+  // graph's root node); `seed` then only carries the batch's offset within the queue.
+  if (seed_cell != nullptr) seed += __ldg(seed_cell);
+  const int first = blockIdx.x * kPerCta;
+  // Cross-kernel software pipeline: while this batch is being scheduled, pull the CTA's slice of
+  // a LATER batch of the same queue from HBM into the 126 MB L2 with one TMA-family bulk
+  // prefetch (every descriptor still crosses HBM exactly once; it just does so while this
+  // kernel is busy with its class lookups and stores, so HBM never idles at kernel boundaries).
+  if (prefetch != nullptr && threadIdx.x == 0) {
+    const int n = min(kPerCta, R - first);
+    if (n > 0) {
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;"
+                   :: "l"(prefetch + first), "r"(n * 16) : "memory");
+    }
+  }
+  // Batches of one queue are independent: let the next batch's grid (launched with programmatic
+  // stream serialization, see launch_pick) start as soon as SM slots free up.  A no-op for a
+  // normally launched successor.
+  asm volatile("griddepcontrol.launch_dependents;");
+  pick_cta<kPerThread>(reqs, out, R, blockIdx.x, cls, lists, list_stride, A, seed);
+}
+
+// A whole queue of SMALL batches in one launch: blockIdx.y selects the batch.  A batch of a few
+// thousand requests is far below one kernel launch's worth of work (C2: 1024 requests = one CTA),
+// so queues of such batches are merged instead of launched one by one.
+struct QueueItem {
+  const int4* reqs;
+  int2* out;
+  uint64_t seed;
+};
+
+template <int kPerThread>
+__global__ void __launch_bounds__(kPickThreads, kPerThread <= 4 ? 8 : 4)
+lig_pick_queue_kernel(const QueueItem* __restrict__ items, int R, const uint2* __restrict__ cls,
+                      const uint16_t* __restrict__ lists, int list_stride, int A) {
+  const QueueItem* it = items + blockIdx.y;
+  const int4* reqs = reinterpret_cast<const int4*>(__ldg(reinterpret_cast<const unsigned long long*>(&it->reqs)));
+  int2* out = reinterpret_cast<int2*>(__ldg(reinterpret_cast<const unsigned long long*>(&it->out)));
+  const uint64_t seed = __ldg(reinterpret_cast<const unsigned long long*>(&it->seed));
+  pick_cta<kPerThread>(reqs, out, R, blockIdx.x, cls, lists, list_stride, A, seed);
+}
+
+// Root node of a cached queue graph: publishes the call's seed to the graph's kernels.
+__global__ void lig_set_seed_kernel(uint64_t* cell, uint64_t value) { *cell = value; }
 
 // ---- K1: direct scan -------------------------------------------------------------------------------
 template <bool kStaged>

@@ -428,3 +428,55 @@ def test_thresholds_are_parameters(engine, oracle):
     finally:
         engine.set_thresholds()
         oracle.set_thresholds()
+
+
+def test_batch_queue_graph_replay_matches_single_batches(engine):
+    """lig_schedule_batches_device: a queue of resident batches (forked streams or a cached CUDA
+    graph replay, L2 prefetch of the next batch) gives exactly the per-batch results, for the first
+    build, for a replay with another seed, and after the snapshot in the slot changed."""
+    import torch
+    c = WL.CONFIGS["C3"]
+    snap = WL.make_snapshot(c["P"], c["A"], seed=41)
+    R, nb = 150_000, 7            # above LIG_MERGE_MAX (131072): per-batch launches / graph path
+    host = [WL.make_requests(R, c["A"], seed=100 + b) for b in range(nb)]
+    d_reqs = [torch.from_numpy(h.view(np.uint8).reshape(-1)).cuda() for h in host]
+    d_out = [torch.zeros(R * 8, dtype=torch.uint8, device="cuda") for _ in range(nb)]
+    stream = torch.cuda.Stream()
+    ep = next_epoch()
+    engine.upload_snapshot(ep, snap.packed)
+
+    def run_queue(epoch, seed):
+        with torch.cuda.stream(stream):
+            engine.schedule_batches_device(epoch, seed, [t.data_ptr() for t in d_reqs], R,
+                                           [t.data_ptr() for t in d_out], stream.cuda_stream)
+        stream.synchronize()
+        return [t.cpu().numpy().view(PICK_DTYPE).copy() for t in d_out]
+
+    for seed in (5, 5, 9000):                       # build, replay, replay with a new seed
+        got = run_queue(ep, seed)
+        for b in range(nb):
+            assert np.array_equal(got[b], engine.schedule_batch(ep, seed + b, host[b])), (seed, b)
+    # a different snapshot uploaded over the older slot: the cached graph must see the new tables
+    snap2 = WL.make_snapshot(c["P"], c["A"], seed=42)
+    ep2, ep3 = next_epoch(), next_epoch()
+    engine.upload_snapshot(ep2, snap2.packed)
+    engine.upload_snapshot(ep3, snap.packed)        # evicts `ep`
+    for epoch in (ep2, ep3):
+        got = run_queue(epoch, 77)
+        for b in range(nb):
+            assert np.array_equal(got[b], engine.schedule_batch(epoch, 77 + b, host[b])), (epoch, b)
+    # small batches take the merged single-launch path (blockIdx.y = batch), ragged R included
+    for Rs in (1, 1000, 1024, 4097):
+        with torch.cuda.stream(stream):
+            engine.schedule_batches_device(ep3, 500, [t.data_ptr() for t in d_reqs], Rs,
+                                           [t.data_ptr() for t in d_out], stream.cuda_stream)
+        stream.synchronize()
+        for b in range(nb):
+            got_b = d_out[b][: Rs * 8].cpu().numpy().view(PICK_DTYPE)
+            assert np.array_equal(got_b, engine.schedule_batch(ep3, 500 + b, host[b][:Rs])), (Rs, b)
+    # short queues (below the graph threshold) and a single batch
+    with torch.cuda.stream(stream):
+        engine.schedule_batches_device(ep3, 3, [d_reqs[0].data_ptr(), d_reqs[1].data_ptr()], R,
+                                       [d_out[0].data_ptr(), d_out[1].data_ptr()], stream.cuda_stream)
+    stream.synchronize()
+    assert np.array_equal(d_out[1].cpu().numpy().view(PICK_DTYPE), engine.schedule_batch(ep3, 4, host[1]))
