@@ -251,6 +251,7 @@ int launch_pick(lig_ctx* c, const Slot& s, uint64_t seed, const lig_req* d_reqs,
     case 1: e = launch_pick_variant<1>(grid, stream, overlap_prev, in, out, R, cls, s.d_lists, stride, s.A, seed, pf); break;
     case 2: e = launch_pick_variant<2>(grid, stream, overlap_prev, in, out, R, cls, s.d_lists, stride, s.A, seed, pf); break;
     case 8: e = launch_pick_variant<8>(grid, stream, overlap_prev, in, out, R, cls, s.d_lists, stride, s.A, seed, pf); break;
+    case 16: e = launch_pick_variant<16>(grid, stream, overlap_prev, in, out, R, cls, s.d_lists, stride, s.A, seed, pf); break;
     default: e = launch_pick_variant<4>(grid, stream, overlap_prev, in, out, R, cls, s.d_lists, stride, s.A, seed, pf); break;
   }
   CUDA_TRY(e);
@@ -328,6 +329,7 @@ int build_queue_graph(const Slot& s, QueueGraph* g, int n_batches) {
     case 1: fn = pick_kernel_ptr<1>(); break;
     case 2: fn = pick_kernel_ptr<2>(); break;
     case 8: fn = pick_kernel_ptr<8>(); break;
+    case 16: fn = pick_kernel_ptr<16>(); break;
     default: fn = pick_kernel_ptr<4>(); break;
   }
   const uint2* cls = reinterpret_cast<const uint2*>(s.d_cls);
@@ -545,7 +547,7 @@ static int create_impl(lig_ctx* c, int device, int max_pods, int max_adapters, i
   }
   if (const char* e = getenv("LIG_PICK_PER_THREAD")) {
     int v2 = atoi(e);
-    if (v2 == 1 || v2 == 2 || v2 == 4 || v2 == 8) c->pick_per_thread = v2;
+    if (v2 == 1 || v2 == 2 || v2 == 4 || v2 == 8 || v2 == 16) c->pick_per_thread = v2;
   }
   if (const char* e = getenv("LIG_PDL")) c->use_pdl = atoi(e) != 0;
   if (const char* e = getenv("LIG_GRAPH")) c->use_graph = atoi(e) != 0;
@@ -767,6 +769,7 @@ int lig_schedule_batches_device(lig_ctx* c, uint64_t epoch, uint64_t seed,
         case 1: lig_pick_queue_kernel<1><<<grid, kPickThreads, 0, st>>>(c->d_items[slot], R, cls, s->d_lists, stride, s->A); break;
         case 2: lig_pick_queue_kernel<2><<<grid, kPickThreads, 0, st>>>(c->d_items[slot], R, cls, s->d_lists, stride, s->A); break;
         case 8: lig_pick_queue_kernel<8><<<grid, kPickThreads, 0, st>>>(c->d_items[slot], R, cls, s->d_lists, stride, s->A); break;
+        case 16: lig_pick_queue_kernel<16><<<grid, kPickThreads, 0, st>>>(c->d_items[slot], R, cls, s->d_lists, stride, s->A); break;
         default: lig_pick_queue_kernel<4><<<grid, kPickThreads, 0, st>>>(c->d_items[slot], R, cls, s->d_lists, stride, s->A); break;
       }
       CUDA_TRY(cudaGetLastError());

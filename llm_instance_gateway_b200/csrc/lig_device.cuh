@@ -820,7 +820,43 @@ __device__ __forceinline__ void pick_cta(const int4* __restrict__ reqs, int2* __
   const int first = cta * kPerCta;
   const int4* src = reqs + first + threadIdx.x;
   int2* dst = out + first + threadIdx.x;
-  int4 r[kPerThread];
+  if constexpr (kPerThread > 4) {
+    // Software-pipelined form: kPerThread = kIter x kWidth; the loads of iteration i+1 are in
+    // flight while iteration i is being scheduled, so one batch needs only R / kPerThread
+    // threads and two consecutive batches of a queue are co-resident on the SMs.
+    constexpr int kWidth = kPerThread / 4;
+    constexpr int kIter = 4;
+    if (first + kPerCta <= R) {
+      int4 cur[kWidth], nxt[kWidth];
+#pragma unroll
+      for (int j = 0; j < kWidth; ++j) cur[j] = ld_stream_int4(src + j * kPickThreads);
+#pragma unroll
+      for (int it = 0; it < kIter; ++it) {
+        if (it + 1 < kIter) {
+#pragma unroll
+          for (int j = 0; j < kWidth; ++j)
+            nxt[j] = ld_stream_int4(src + ((it + 1) * kWidth + j) * kPickThreads);
+        }
+#pragma unroll
+        for (int j = 0; j < kWidth; ++j)
+          st_stream_int2(dst + (it * kWidth + j) * kPickThreads,
+                         pick_one(cur[j], cls, lists, (uint32_t)list_stride, (uint32_t)A, seed));
+#pragma unroll
+        for (int j = 0; j < kWidth; ++j) cur[j] = nxt[j];
+      }
+      return;
+    }
+#pragma unroll 1
+    for (int j = 0; j < kPerThread; ++j) {   // ragged tail CTA
+      const int i = first + threadIdx.x + j * kPickThreads;
+      if (i < R)
+        st_stream_int2(dst + j * kPickThreads,
+                       pick_one(ld_stream_int4(src + j * kPickThreads), cls, lists,
+                                (uint32_t)list_stride, (uint32_t)A, seed));
+    }
+    return;
+  }
+  int4 r[kPerThread > 4 ? 1 : kPerThread];
   if (first + kPerCta <= R) {              // full CTA: no per-request bounds checks
 #pragma unroll
     for (int j = 0; j < kPerThread; ++j) r[j] = ld_stream_int4(src + j * kPickThreads);
@@ -842,7 +878,7 @@ __device__ __forceinline__ void pick_cta(const int4* __restrict__ reqs, int2* __
 
 // 8 CTAs/SM (<= 32 registers) so a 2^20-request batch (1024 CTAs) is a single wave on 148 SMs.
 template <int kPerThread>
-__global__ void __launch_bounds__(kPickThreads, kPerThread <= 4 ? 8 : 4)
+__global__ void __launch_bounds__(kPickThreads, kPerThread <= 8 ? 8 : 6)
 lig_pick_stream_kernel(const int4* __restrict__ reqs, int2* __restrict__ out, int R,
                        const uint2* __restrict__ cls, const uint16_t* __restrict__ lists,
                        int list_stride, int A, uint64_t seed, const int4* __restrict__ prefetch,
@@ -880,7 +916,7 @@ struct QueueItem {
 };
 
 template <int kPerThread>
-__global__ void __launch_bounds__(kPickThreads, kPerThread <= 4 ? 8 : 4)
+__global__ void __launch_bounds__(kPickThreads, kPerThread <= 8 ? 8 : 6)
 lig_pick_queue_kernel(const QueueItem* __restrict__ items, int R, const uint2* __restrict__ cls,
                       const uint16_t* __restrict__ lists, int list_stride, int A) {
   const QueueItem* it = items + blockIdx.y;
