@@ -139,6 +139,15 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------
+def cpu_quota():
+    """cgroup CPU quota of this container in cores (None = unlimited), to read `cores` honestly."""
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        return None if quota == "max" else float(quota) / float(period)
+    except Exception:
+        return None
+
+
 def cpu_reference_rate(snap, reqs, seed, nthreads, seconds):
     """Time the oracle port (the reference's algorithm and data structures, in C) on a bounded
     sample of the workload.  Returns (decisions/s, sample size)."""
@@ -230,7 +239,8 @@ def run_reference(args, cfg, R):
                    "requests_per_gpu": R, "pods": cfg["P"], "adapters": cfg["A"],
                    "note": "C restatement of the Go scheduler (Go toolchain absent): same tree, pointer "
                            "slices, string-keyed ActiveModels maps, fresh slice per stage; all host threads"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": nthreads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": nthreads, "kind": "port", "sample": sample,
+                         "cgroup_cpu_quota_cores": cpu_quota()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -425,7 +435,7 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": ms_region / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
-            "dtype": "int32/u64 index arithmetic + f64 compares", "data": "synthetic",
+            "dtype": "int32+u64+f64", "data": "synthetic",
             "config": {
                 "workload": workload_label(args.workload, R, P, A),
                 "requests_per_gpu": R, "pods": P, "adapters": A, "parallelism": f"request-sharded x{world}",
@@ -463,6 +473,7 @@ def main():
                 "value": v, "unit": UNIT, "cores": nthreads, "kind": "port",
                 "sample": f"first {sample} requests of batch 0 of the same workload",
                 "single_thread": {"value": v1, "sample": sample1},
+                "cgroup_cpu_quota_cores": cpu_quota(),
                 "note": "C restatement of the Go scheduler with the reference's data structures "
                         "(Go toolchain absent from the image)"}
         print(json.dumps(line))
