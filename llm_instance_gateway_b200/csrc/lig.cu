@@ -493,13 +493,21 @@ int lig_pack_snapshot(void* blob, int P, int A, const double* kv, const int32_t*
   if (A > 0 && P > 0 && !bitmap) return fail(LIG_ERR_INVALID, "null bitmap");
   const Layout l = layout_for(P, A);
   unsigned char* b = static_cast<unsigned char*>(blob);
-  memset(b, 0, l.total);
+  if (P == 0) memset(b, 0, l.total);
   if (P > 0) {
+    // copy the P real pods and zero only the padding pods of each column (no full-blob memset)
+    const size_t pad = (size_t)words_for(P) * 32 - (size_t)P;
     memcpy(b + l.kv, kv, (size_t)P * sizeof(double));
+    memset(b + l.kv + (size_t)P * sizeof(double), 0, pad * sizeof(double));
     memcpy(b + l.q, q, (size_t)P * sizeof(int32_t));
+    memset(b + l.q + (size_t)P * sizeof(int32_t), 0, pad * sizeof(int32_t));
     memcpy(b + l.na, na, (size_t)P * sizeof(uint16_t));
+    memset(b + l.na + (size_t)P * sizeof(uint16_t), 0, pad * sizeof(uint16_t));
     memcpy(b + l.ma, ma, (size_t)P * sizeof(uint16_t));
-    if (A > 0) memcpy(b + l.bitmap, bitmap, (size_t)A * words_for(P) * sizeof(uint32_t));
+    memset(b + l.ma + (size_t)P * sizeof(uint16_t), 0, pad * sizeof(uint16_t));
+    const size_t bm_bytes = (size_t)A * words_for(P) * sizeof(uint32_t);
+    if (A > 0) memcpy(b + l.bitmap, bitmap, bm_bytes);
+    memset(b + l.bitmap + bm_bytes, 0, l.total - l.bitmap - bm_bytes);
     // bits of padding pods must be clear in the last word of every row
     const int W = words_for(P), rem = P & 31;
     if (rem) {

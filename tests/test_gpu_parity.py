@@ -400,6 +400,19 @@ def test_device_pointer_api_matches_host_api(engine):
     pin_out = torch.zeros(R * 8, dtype=torch.uint8).pin_memory()
     engine.schedule_batch_ptr(ep, 77, pin_in.data_ptr(), R, pin_out.data_ptr())
     assert np.array_equal(pin_out.numpy().view(PICK_DTYPE), want)
+    # a big pinned batch (zero-copy), the pageable bounce path and the device path agree
+    R2 = 300_001
+    reqs2 = WL.make_requests(R2, c["A"], seed=77)
+    want2 = engine.schedule_batch(ep, 78, reqs2)                      # pageable: bounce path
+    pin_in2 = torch.from_numpy(reqs2.view(np.uint8).reshape(-1)).pin_memory()
+    pin_out2 = torch.zeros(R2 * 8, dtype=torch.uint8).pin_memory()
+    engine.schedule_batch_ptr(ep, 78, pin_in2.data_ptr(), R2, pin_out2.data_ptr())
+    assert np.array_equal(pin_out2.numpy().view(PICK_DTYPE), want2)
+    d2 = torch.from_numpy(reqs2.view(np.uint8).reshape(-1)).cuda()
+    o2 = torch.zeros(R2 * 8, dtype=torch.uint8, device="cuda")
+    engine.schedule_batch_device(ep, 78, d2.data_ptr(), R2, o2.data_ptr(), 0)
+    torch.cuda.synchronize()
+    assert np.array_equal(o2.cpu().numpy().view(PICK_DTYPE), want2)
     # snapshot upload from a blob already in HBM (the NCCL-broadcast path)
     blob = torch.from_numpy(snap.packed.blob()).cuda()
     ep2 = next_epoch()
