@@ -107,41 +107,47 @@ struct lig_ctx {
   int sm_count = 0;
   size_t smem_optin = 0;
   lig_thresholds thr{0.8, 5, 50};
+  std::mutex mu;                             // guards everything below
+  std::atomic<uint64_t> launches{0};
+
+  // ---- snapshots: two resident epochs ----
   Slot slot[2];
   uint64_t stamp = 0;
   cudaStream_t s_up = nullptr;               // snapshot uploads + table builds
-  cudaStream_t s_pipe[kPipeStreams] = {};    // host-buffer batches
-  lig_req* d_reqs = nullptr;                 // device staging for host-buffer batches
+
+  // ---- host-buffer batches ----
+  cudaStream_t s_pipe[kPipeStreams] = {};    // also the queue streams of lig_schedule_batches_device
+  lig_req* d_reqs = nullptr;                 // device staging (scan test hook)
   lig_pick* d_out = nullptr;
   uint32_t* d_masks = nullptr;               // scan test hook staging (lazily sized)
   size_t d_masks_bytes = 0;
-  lig_req* h_reqs = nullptr;                 // pinned bounce buffers for pageable callers
+  lig_req* h_reqs = nullptr;                 // pinned, device-mapped bounce buffers for pageable callers
   lig_pick* h_out = nullptr;
-  std::atomic<uint64_t> launches{0};
-  std::mutex mu;
-  // tuning knobs (env LIG_PICK_PER_THREAD = 1|2|4, LIG_QUEUE_STREAMS = 1..3), read at create
-  int pick_per_thread = 4;
-  int queue_streams = 4;
-  bool use_pdl = false;  // env LIG_PDL=1: programmatic dependent launch inside batch queues
-  int prefetch_distance = 1;  // env LIG_PREFETCH=d (0 = off): batch b pulls batch b+d of the same queue into L2
+
+  // ---- batch queues (lig_schedule_batches_device) ----
   cudaEvent_t fork = nullptr;
   cudaEvent_t join[kPipeStreams] = {};
-  // cached CUDA graphs of batch queues (env LIG_GRAPH=0 disables): a queue with the same
-  // buffers, shape and snapshot slot is replayed with one cudaGraphLaunch instead of one
-  // cudaLaunchKernel per batch
-  bool use_graph = true;
-  int graph_min_batches = 4;
-  // queues of small batches (R <= merge_max_requests, env LIG_MERGE_MAX) run as ONE launch with
-  // blockIdx.y = batch; the item table goes through a small pinned ring
-  int merge_max_requests = 1 << 17;
+  // cached CUDA graphs: a queue with the same buffers, shape and snapshot slot is replayed with
+  // one cudaGraphLaunch instead of one cudaLaunchKernel per batch
+  std::vector<QueueGraph*> graphs;
+  uint64_t graph_clock = 0;
+  // queues of small batches run as ONE launch with blockIdx.y = batch; the item table goes
+  // through a small pinned ring
   static constexpr int kItemSlots = 4;
   static constexpr int kMaxItems = 65535;
   QueueItem* d_items[kItemSlots] = {};
   QueueItem* h_items[kItemSlots] = {};
   cudaEvent_t items_free[kItemSlots] = {};
   int item_slot = 0;
-  std::vector<struct QueueGraph*> graphs;
-  uint64_t graph_clock = 0;
+
+  // ---- tuning knobs, read from the environment at lig_create ----
+  int pick_per_thread = 4;          // LIG_PICK_PER_THREAD = 1|2|4 (plain) | 8|16 (software-pipelined)
+  int queue_streams = 4;            // LIG_QUEUE_STREAMS   = 1..8 streams a queue is forked over
+  bool use_pdl = false;             // LIG_PDL=1           programmatic dependent launch inside a queue
+  int prefetch_distance = 1;        // LIG_PREFETCH=d      batch b pulls batch b+d of the queue into L2 (0 = off)
+  bool use_graph = true;            // LIG_GRAPH=0         disable cached graph replay of queues
+  int graph_min_batches = 4;
+  int merge_max_requests = 1 << 17; // LIG_MERGE_MAX       largest R whose queues run as one merged launch
 };
 
 namespace {

@@ -121,3 +121,33 @@ def test_refresh_follows_the_provider():
     assert s.Schedule("m", "m", True)[1].Name == "pod-1"
     s.close()
     prov.close()
+
+
+@pytest.mark.gpu
+def test_reference_load_test_shape(oracle):
+    """The reference's ghz load generator (pkg/ext-proc/test/benchmark/benchmark.go:20-29,45-110):
+    200 fake pods, 5 adapters each ("adapter-<pod*5+j>"), all other metrics zero, requests cycling
+    over the 1000 adapter names, no Criticality.  With MaxActiveModels == 0 nobody has room, so the
+    only low-cost pod is the one holding the adapter: request n must land on pod (n % 1000) // 5."""
+    n_pods, per_pod = 200, 5
+    pods = [PodMetrics(Pod(f"pod-{i}", f"address-{i}"),
+                       Metrics(ActiveModels={f"adapter-{i * per_pod + j}": 0 for j in range(per_pod)}))
+            for i in range(n_pods)]
+    prov = H.HostProvider(pods)
+    s = H.HostScheduler(prov, max_pods=256, max_adapters=1024, max_batch=4096, flush_size=512,
+                        batch_window_us=20, busy_poll=True, caller_spin_us=50)
+    models = [f"adapter-{m}" for m in range(n_pods * per_pod)]
+    codes, picked = s.schedule_concurrent(50, 400, models, [False] * len(models))
+    assert (codes == H.GRPC_OK).all()
+    want = np.array([(i % len(models)) // per_pod for i in range(len(codes))])
+    assert np.array_equal(picked, want)
+    # and the oracle agrees on a sample of the same requests
+    pool = oracle.Pool([dict(name=p.Pod.Name, address=p.Pod.Address, waiting_queue_size=0,
+                             kv_cache_usage_percent=0.0, max_active_models=0,
+                             active_models=list(p.Metrics.ActiveModels)) for p in pods])
+    for m in (0, 4, 5, 499, 999):
+        assert pool.filter(models[m], False) == (oracle.LIGO_OK, [m // per_pod])
+    st = s.stats()
+    assert st["scheduled"] == len(codes) and st["batches"] < len(codes)
+    s.close()
+    prov.close()
