@@ -184,6 +184,20 @@ int lig_schedule_batches_device(lig_ctx* ctx, uint64_t epoch, uint64_t seed,
                                 const lig_req* const* d_reqs, int R, lig_pick* const* d_out,
                                 int n_batches, void* stream);
 
+/* ---- streaming micro-batches without a kernel launch ---------------------------------------------
+ * lig_stream_open parks one persistent CTA on the device that polls a mailbox in page-locked host
+ * memory; lig_stream_submit writes up to lig_stream_capacity() descriptors + a doorbell ticket
+ * into it and spins until the picks and the completion ticket are back: two PCIe crossings, no
+ * launch, no stream synchronisation (Scheduler.Schedule under a sustained request stream,
+ * handlers/request.go:72).  Same results as lig_schedule_batch for the same (epoch, seed, reqs).
+ * While a stream is open nothing in the process may synchronise the whole device
+ * (cudaDeviceSynchronize, cudaFree): the resident kernel never finishes until lig_stream_close. */
+int lig_stream_capacity(void);
+int lig_stream_open(lig_ctx* ctx);
+int lig_stream_submit(lig_ctx* ctx, uint64_t epoch, uint64_t seed, const lig_req* reqs, int n,
+                      lig_pick* out);
+int lig_stream_close(lig_ctx* ctx);
+
 /* Direct scan: every request walks the whole tree over all P pods itself (one warp per request,
  * no class tables).  d_masks, when not NULL, receives the survivor set of every request as
  * R x ceil(P/32) words (bit p%32 of word p/32 = pod p survives) — the GPU analogue of

@@ -23,6 +23,7 @@ EXPORTED_SYMBOLS = (
     "lig_schedule_batch", "lig_schedule_batch_device", "lig_schedule_batches_device", "lig_schedule_scan_device",
     "lig_schedule_scan", "lig_read_class", "lig_last_error", "lig_version", "lig_abi_version",
     "lig_device_count", "lig_kernel_launches", "lig_sm_count", "lig_host_alloc", "lig_host_free",
+    "lig_stream_capacity", "lig_stream_open", "lig_stream_submit", "lig_stream_close",
 )
 
 
@@ -86,6 +87,9 @@ def load() -> C.CDLL:
     lib.lig_host_alloc.restype = vp
     lib.lig_host_free.argtypes = [vp]
     lib.lig_host_free.restype = None
+    lib.lig_stream_open.argtypes = [vp]
+    lib.lig_stream_submit.argtypes = [vp, u64, u64, vp, i32, vp]
+    lib.lig_stream_close.argtypes = [vp]
     for name in EXPORTED_SYMBOLS:
         getattr(lib, name)  # AttributeError if the library does not export it
     _lib = lib

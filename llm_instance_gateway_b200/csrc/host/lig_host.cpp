@@ -53,6 +53,7 @@ Status NewScheduler(std::shared_ptr<PodMetricsProvider> pmp, const Options& opt,
   s->rng_state_ = seed ^ 0xD1B54A32D192ED03ull;
   Status st = s->Refresh();
   if (!st.ok()) return st;
+  if (opt.use_doorbell && lig_stream_open(s->ctx_) != 0) return LigFailure("lig_stream_open");
   s->batcher_ = std::thread(&Scheduler::BatcherLoop, s.get());
   if (opt.refresh_interval.count() > 0) s->refresher_ = std::thread(&Scheduler::RefresherLoop, s.get());
   *out = std::move(s);
@@ -68,6 +69,7 @@ Scheduler::~Scheduler() {
   cv_.notify_all();
   if (batcher_.joinable()) batcher_.join();
   if (refresher_.joinable()) refresher_.join();
+  if (ctx_ && opt_.use_doorbell) lig_stream_close(ctx_);
   if (h_reqs_) lig_host_free(h_reqs_);
   if (h_picks_) lig_host_free(h_picks_);
   if (ctx_) lig_destroy(ctx_);
@@ -212,7 +214,9 @@ void Scheduler::Flush(std::vector<Waiter*>& batch) {
         h_reqs_[i].flags = r.Critical ? LIG_REQ_CRITICAL : 0u;
         h_reqs_[i].rand_key = splitmix_next(rng_state_);
       }
-      rc = lig_schedule_batch(ctx_, snap->epoch, seed_, h_reqs_, n, h_picks_);
+      rc = (opt_.use_doorbell && n <= lig_stream_capacity())
+               ? lig_stream_submit(ctx_, snap->epoch, seed_, h_reqs_, n, h_picks_)
+               : lig_schedule_batch(ctx_, snap->epoch, seed_, h_reqs_, n, h_picks_);
       if (rc != LIG_ERR_STALE_EPOCH) break;   // two refreshes raced past this batch: re-resolve
       std::lock_guard<std::mutex> sk(stats_mu_);
       stats_.stale_retries++;

@@ -94,6 +94,9 @@ struct Options {
   std::chrono::milliseconds refresh_interval{0};
   // Latency knobs: the batcher thread polls its queue instead of sleeping on a condition
   // variable, and callers spin this long on their result before blocking in the kernel.
+  // Flush micro-batches through the persistent doorbell kernel (lig_stream_submit) instead of a
+  // kernel launch per flush.  Nothing else in the process may then synchronise the whole device.
+  bool use_doorbell = false;
   bool busy_poll = false;
   std::chrono::microseconds caller_spin{0};
   double kv_cache_threshold = 0.8;   // scheduler.go:15-24

@@ -67,8 +67,8 @@ int ligh_provider_set_pods(ligh_provider* p, int n, const char* const* names, co
 
 ligh_scheduler* ligh_scheduler_new2(ligh_provider* p, int device, int max_pods, int max_adapters,
                                     int max_batch, int flush_size, int window_us, int refresh_ms,
-                                    uint64_t seed, int busy_poll, int caller_spin_us, char* err,
-                                    int err_cap) {
+                                    uint64_t seed, int busy_poll, int caller_spin_us,
+                                    int use_doorbell, char* err, int err_cap) {
   scheduling::Options o;
   o.device = device;
   o.max_pods = max_pods;
@@ -80,6 +80,7 @@ ligh_scheduler* ligh_scheduler_new2(ligh_provider* p, int device, int max_pods, 
   o.seed = seed;
   o.busy_poll = busy_poll != 0;
   o.caller_spin = std::chrono::microseconds(caller_spin_us);
+  o.use_doorbell = use_doorbell != 0;
   auto* s = new ligh_scheduler();
   s->provider = share(p);
   scheduling::Status st = scheduling::NewScheduler(s->provider, o, &s->sched);
@@ -95,7 +96,7 @@ ligh_scheduler* ligh_scheduler_new(ligh_provider* p, int device, int max_pods, i
                                    int max_batch, int flush_size, int window_us, int refresh_ms,
                                    uint64_t seed, char* err, int err_cap) {
   return ligh_scheduler_new2(p, device, max_pods, max_adapters, max_batch, flush_size, window_us,
-                             refresh_ms, seed, 0, 0, err, err_cap);
+                             refresh_ms, seed, 0, 0, 0, err, err_cap);
 }
 
 void ligh_scheduler_free(ligh_scheduler* s) { delete s; }

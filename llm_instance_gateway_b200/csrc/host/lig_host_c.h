@@ -22,11 +22,12 @@ int ligh_provider_set_pods(ligh_provider*, int n, const char* const* names, cons
 ligh_scheduler* ligh_scheduler_new(ligh_provider*, int device, int max_pods, int max_adapters,
                                    int max_batch, int flush_size, int batch_window_us,
                                    int refresh_interval_ms, uint64_t seed, char* err, int err_cap);
-/* Same, plus the latency knobs: busy_poll (batcher polls instead of sleeping), caller_spin_us. */
+/* Same, plus the latency knobs: busy_poll (batcher polls instead of sleeping), caller_spin_us,
+ * use_doorbell (flush through the persistent doorbell kernel instead of a launch per flush). */
 ligh_scheduler* ligh_scheduler_new2(ligh_provider*, int device, int max_pods, int max_adapters,
                                     int max_batch, int flush_size, int batch_window_us,
                                     int refresh_interval_ms, uint64_t seed, int busy_poll,
-                                    int caller_spin_us, char* err, int err_cap);
+                                    int caller_spin_us, int use_doorbell, char* err, int err_cap);
 void ligh_scheduler_free(ligh_scheduler*);
 /* Scheduler.Schedule: returns the gRPC code (0 OK, 8 ResourceExhausted, 2 Unknown, 13 Internal). */
 int ligh_schedule(ligh_scheduler*, const char* model, const char* resolved_target_model, int critical,

@@ -8,6 +8,7 @@
 
 #include <atomic>
 #include <cstdarg>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -139,6 +140,13 @@ struct lig_ctx {
   QueueItem* h_items[kItemSlots] = {};
   cudaEvent_t items_free[kItemSlots] = {};
   int item_slot = 0;
+
+  // ---- streaming doorbell (lig_stream_open): a persistent kernel polling a host mailbox ----
+  Mailbox* mailbox = nullptr;       // pinned, device-mapped
+  Mailbox* d_mailbox = nullptr;     // its device alias
+  cudaStream_t s_doorbell = nullptr;
+  uint32_t next_ticket = 1;
+  bool stream_open = false;
 
   // ---- tuning knobs, read from the environment at lig_create ----
   int pick_per_thread = 4;          // LIG_PICK_PER_THREAD = 1|2|4 (plain) | 8|16 (software-pipelined)
@@ -380,6 +388,8 @@ QueueGraph* queue_graph_for(lig_ctx* c, const Slot& s, const lig_req* const* d_r
     g->last_use = ++c->graph_clock;
     return g;
   }
+  if (c->graphs.size() >= kMaxQueueGraphs && c->stream_open)
+    return nullptr;   // eviction needs a device-wide synchronise, impossible under a resident kernel
   if (c->graphs.size() >= kMaxQueueGraphs) {   // evict the least recently used
     size_t victim = 0;
     for (size_t i = 1; i < c->graphs.size(); ++i)
@@ -624,6 +634,7 @@ int lig_create(lig_ctx** out, int device, int max_pods, int max_adapters, int ma
 void lig_destroy(lig_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
+  lig_stream_close(c);   // a resident doorbell kernel would make the synchronize below wait forever
   cudaDeviceSynchronize();
   for (auto& s : c->slot) {
     cudaFree(s.d_blob);
@@ -633,6 +644,8 @@ void lig_destroy(lig_ctx* c) {
     if (s.ready) cudaEventDestroy(s.ready);
     if (s.idle) cudaEventDestroy(s.idle);
   }
+  if (c->mailbox) cudaFreeHost(c->mailbox);
+  if (c->s_doorbell) cudaStreamDestroy(c->s_doorbell);
   for (int i = 0; i < lig_ctx::kItemSlots; ++i) {
     cudaFree(c->d_items[i]);
     cudaFreeHost(c->h_items[i]);
@@ -900,6 +913,9 @@ int lig_schedule_scan(lig_ctx* c, uint64_t epoch, uint64_t seed, const lig_req* 
   cudaStream_t st = c->s_pipe[0];
   const size_t mask_bytes = masks ? (size_t)R * (s->W > 0 ? s->W : 1) * sizeof(uint32_t) : 0;
   if (mask_bytes > c->d_masks_bytes) {
+    if (c->stream_open)
+      return fail(LIG_ERR_INVALID, "lig_schedule_scan: cannot grow the mask buffer while a stream is open "
+                                   "(cudaFree would wait for the resident doorbell kernel)");
     CUDA_TRY(cudaStreamSynchronize(st));
     cudaFree(c->d_masks);
     c->d_masks = nullptr;
@@ -957,6 +973,79 @@ void lig_host_free(void* p) {
   if (!p) return;
   unregister_pinned(p);
   cudaFreeHost(p);
+}
+
+int lig_stream_capacity(void) { return kMailboxCapacity; }
+
+int lig_stream_open(lig_ctx* c) {
+  if (!c) return fail(LIG_ERR_INVALID, "lig_stream_open: ctx is null");
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (c->stream_open) return 0;
+  CUDA_TRY(cudaSetDevice(c->device));
+  if (!c->mailbox) {
+    CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&c->mailbox), sizeof(Mailbox), cudaHostAllocMapped));
+    CUDA_TRY(cudaHostGetDevicePointer(reinterpret_cast<void**>(&c->d_mailbox), c->mailbox, 0));
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->s_doorbell, cudaStreamNonBlocking));
+  }
+  memset(c->mailbox, 0, offsetof(Mailbox, reqs));
+  c->next_ticket = 1;
+  std::atomic_thread_fence(std::memory_order_seq_cst);
+  lig_doorbell_kernel<<<1, kPickThreads, 0, c->s_doorbell>>>(c->d_mailbox);
+  CUDA_TRY(cudaGetLastError());
+  c->launches++;
+  c->stream_open = true;
+  return 0;
+}
+
+int lig_stream_close(lig_ctx* c) {
+  if (!c) return fail(LIG_ERR_INVALID, "lig_stream_close: ctx is null");
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (!c->stream_open) return 0;
+  CUDA_TRY(cudaSetDevice(c->device));
+  reinterpret_cast<std::atomic<uint32_t>*>(&c->mailbox->ticket)->store(kMailboxQuit, std::memory_order_release);
+  CUDA_TRY(cudaStreamSynchronize(c->s_doorbell));
+  c->stream_open = false;
+  return 0;
+}
+
+int lig_stream_submit(lig_ctx* c, uint64_t epoch, uint64_t seed, const lig_req* reqs, int n,
+                      lig_pick* out) {
+  if (!c || n < 0 || (n > 0 && (!reqs || !out)))
+    return fail(LIG_ERR_INVALID, "lig_stream_submit: bad argument");
+  if (n > kMailboxCapacity)
+    return fail(LIG_ERR_INVALID, "n=%d exceeds the doorbell capacity %d", n, kMailboxCapacity);
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (!c->stream_open) return fail(LIG_ERR_INVALID, "lig_stream_submit: call lig_stream_open first");
+  Slot* s = nullptr;
+  if (int rc = resolve_slot(c, epoch, &s)) return rc;
+  if (n == 0) return 0;
+  CUDA_TRY(cudaSetDevice(c->device));
+  // the tables of this slot must be complete before the resident kernel reads them; uploads
+  // through the host API have already synchronised, device-side uploads are waited for here
+  CUDA_TRY(cudaEventSynchronize(s->ready));
+  Mailbox* mb = c->mailbox;
+  memcpy(mb->reqs, reqs, (size_t)n * sizeof(lig_req));
+  mb->count = (uint32_t)n;
+  mb->A = (uint32_t)s->A;
+  mb->list_stride = (uint32_t)(s->P > 0 ? s->P : 1);
+  mb->seed = seed;
+  mb->cls = reinterpret_cast<const uint2*>(s->d_cls);
+  mb->lists = s->d_lists;
+  const uint32_t ticket = c->next_ticket++;
+  reinterpret_cast<std::atomic<uint32_t>*>(&mb->ticket)->store(ticket, std::memory_order_release);
+  auto* done = reinterpret_cast<std::atomic<uint32_t>*>(&mb->done);
+  uint64_t spins = 0;
+  while (done->load(std::memory_order_acquire) != ticket) {
+#if defined(__x86_64__)
+    __builtin_ia32_pause();
+#endif
+    if ((++spins & 0xfffff) == 0 && cudaStreamQuery(c->s_doorbell) != cudaErrorNotReady) {
+      c->stream_open = false;   // the resident kernel is gone (error or device reset)
+      return fail(LIG_ERR_CUDA, "doorbell kernel is not running: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+  }
+  memcpy(out, mb->picks, (size_t)n * sizeof(lig_pick));
+  return 0;
 }
 
 uint64_t lig_kernel_launches(const lig_ctx* c) { return c ? c->launches.load() : 0; }

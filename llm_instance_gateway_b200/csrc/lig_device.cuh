@@ -926,6 +926,113 @@ lig_pick_queue_kernel(const QueueItem* __restrict__ items, int R, const uint2* _
   pick_cta<kPerThread>(reqs, out, R, blockIdx.x, cls, lists, list_stride, A, seed);
 }
 
+// ---- K3: persistent doorbell kernel (streaming micro-batches) ------------------------------------
+// One resident CTA polls a mailbox in page-locked host memory.  The host writes the micro-batch
+// (header + descriptors), then the ticket; the CTA schedules it with the same pick_one() and
+// writes the picks and the completion ticket back to host memory.  No kernel launch and no stream
+// synchronisation per micro-batch: the round trip is two PCIe crossings.  Class tables are read
+// with ld.global.cg (L2 only): the kernel outlives snapshot uploads, and L1 is not coherent.
+constexpr int kMailboxCapacity = 4096;   // requests per doorbell
+constexpr uint32_t kMailboxQuit = 0xffffffffu;
+
+struct alignas(64) Mailbox {
+  // --- written by the host ---
+  uint32_t ticket;            // doorbell: last field written (release); kMailboxQuit = leave the kernel
+  uint32_t count;
+  uint32_t A;
+  uint32_t list_stride;
+  uint64_t seed;
+  const uint2* cls;           // device pointers of the snapshot slot to use
+  const uint16_t* lists;
+  uint32_t pad0[6];
+  // --- written by the device ---
+  alignas(64) uint32_t done;  // completion ticket (release)
+  uint32_t pad1[15];
+  alignas(64) lig_req reqs[kMailboxCapacity];
+  alignas(64) lig_pick picks[kMailboxCapacity];
+};
+
+__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys_u32(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int4 ld_sys_int4(const void* p) {
+  int4 r;
+  asm volatile("ld.relaxed.sys.global.v4.s32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+  return r;
+}
+__device__ __forceinline__ uint2 ld_cg_uint2(const uint2* p) {
+  uint2 r;
+  asm volatile("ld.global.cg.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint32_t ld_cg_u16(const uint16_t* p) {
+  uint16_t r;
+  asm volatile("ld.global.cg.u16 %0, [%1];" : "=h"(r) : "l"(p));
+  return r;
+}
+
+__device__ __forceinline__ int2 doorbell_pick(const int4 r, const uint2* cls, const uint16_t* lists,
+                                              uint32_t stride, uint32_t A, uint64_t seed) {
+  const uint32_t critical = (uint32_t)r.y & LIG_REQ_CRITICAL;
+  const uint64_t key = ((uint64_t)(uint32_t)r.w << 32) | (uint32_t)r.z;
+  const uint32_t a = min((uint32_t)r.x, A);
+  const uint32_t c = critical * (A + 1u) + a;
+  const uint2 e = ld_cg_uint2(cls + c);
+  int pod = -1;
+  if (e.x >> 16) {
+    const uint32_t k = int31n_magic(seed ^ key, e.x, e.y);
+    const uint32_t row = class_list_row(e.x, c, 2u * (A + 1u));
+    pod = (int)ld_cg_u16(lists + (row * stride + k));
+  }
+  return make_int2(pod, (int)(e.x & 0xffff0003u));
+}
+
+__global__ void __launch_bounds__(kPickThreads)
+lig_doorbell_kernel(Mailbox* mb) {
+  __shared__ uint32_t s_go;
+  uint32_t ticket = 1;
+  for (;;) {
+    if (threadIdx.x == 0) {
+      uint32_t go = 1;
+      for (;;) {
+        const uint32_t t = ld_acquire_sys_u32(&mb->ticket);
+        if (t == ticket) break;
+        if (t == kMailboxQuit) { go = 0; break; }
+      }
+      s_go = go;
+    }
+    __syncthreads();
+    if (!s_go) return;
+    // One PCIe round trip for everything a small micro-batch needs: the header (same 64-byte
+    // line as the ticket) and this thread's first descriptor are requested together, the
+    // descriptor speculatively (the mailbox always holds kMailboxCapacity slots).
+    const int4 h0 = ld_sys_int4(&mb->ticket);          // ticket, count, A, list_stride
+    const int4 h1 = ld_sys_int4(&mb->seed);            // seed lo/hi, cls lo/hi
+    const int4 h2 = ld_sys_int4(&mb->lists);           // lists lo/hi, pad
+    int4 r = ld_sys_int4(&mb->reqs[threadIdx.x]);
+    const uint32_t count = (uint32_t)h0.y, A = (uint32_t)h0.z, stride = (uint32_t)h0.w;
+    const uint64_t seed = ((uint64_t)(uint32_t)h1.y << 32) | (uint32_t)h1.x;
+    const uint2* cls = reinterpret_cast<const uint2*>(((uint64_t)(uint32_t)h1.w << 32) | (uint32_t)h1.z);
+    const uint16_t* lists = reinterpret_cast<const uint16_t*>(((uint64_t)(uint32_t)h2.y << 32) | (uint32_t)h2.x);
+    for (uint32_t i = threadIdx.x; i < count; i += kPickThreads) {
+      if (i != threadIdx.x) r = ld_sys_int4(&mb->reqs[i]);
+      const int2 p = doorbell_pick(r, cls, lists, stride, A, seed);
+      asm volatile("st.relaxed.sys.global.v2.s32 [%0], {%1, %2};"
+                   :: "l"(reinterpret_cast<int2*>(&mb->picks[i])), "r"(p.x), "r"(p.y) : "memory");
+    }
+    // the barrier orders every thread's pick stores before thread 0's release store (cumulative)
+    __syncthreads();
+    if (threadIdx.x == 0) st_release_sys_u32(&mb->done, ticket);
+    ++ticket;
+  }
+}
+
 // Root node of a cached queue graph: publishes the call's seed to the graph's kernels.
 __global__ void lig_set_seed_kernel(uint64_t* cell, uint64_t value) { *cell = value; }
 

@@ -95,6 +95,19 @@ class Engine:
         N.check(self._lib.lig_schedule_scan_device(self._ctx, epoch, seed, d_reqs, R, d_out,
                                                    d_masks or None, stream or None))
 
+    # ---- streaming doorbell (persistent kernel) ----
+    def stream_open(self) -> None:
+        N.check(self._lib.lig_stream_open(self._ctx))
+
+    def stream_close(self) -> None:
+        N.check(self._lib.lig_stream_close(self._ctx))
+
+    def stream_submit(self, epoch: int, seed: int, reqs: np.ndarray) -> np.ndarray:
+        assert reqs.dtype == REQ_DTYPE and reqs.flags.c_contiguous
+        out = np.empty(len(reqs), dtype=PICK_DTYPE)
+        N.check(self._lib.lig_stream_submit(self._ctx, epoch, seed, _ptr(reqs), len(reqs), _ptr(out)))
+        return out
+
     def read_class(self, epoch: int, critical: bool, adapter_id: int, P: int):
         status, n = C.c_int(), C.c_int()
         lst = np.zeros(max(P, 1), dtype=np.uint16)

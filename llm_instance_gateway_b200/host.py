@@ -45,7 +45,7 @@ def load() -> C.CDLL:
     lib.ligh_provider_set_pods.argtypes = [vp, i32, cpp, cpp, vp, vp, vp, cpp, vp]
     lib.ligh_scheduler_new.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, u64, C.c_char_p, i32]
     lib.ligh_scheduler_new.restype = vp
-    lib.ligh_scheduler_new2.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, u64, i32, i32, C.c_char_p, i32]
+    lib.ligh_scheduler_new2.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, u64, i32, i32, i32, C.c_char_p, i32]
     lib.ligh_scheduler_new2.restype = vp
     lib.ligh_scheduler_free.argtypes = [vp]
     lib.ligh_scheduler_free.restype = None
@@ -109,13 +109,13 @@ class HostScheduler:
     def __init__(self, provider: HostProvider, device: int = 0, max_pods: int = 4096,
                  max_adapters: int = 1024, max_batch: int = 1 << 16, flush_size: int = 4096,
                  batch_window_us: int = 50, refresh_interval_ms: int = 0, seed: int = 1,
-                 busy_poll: bool = False, caller_spin_us: int = 0):
+                 busy_poll: bool = False, caller_spin_us: int = 0, use_doorbell: bool = False):
         self._lib = load()
         self.provider = provider
         err = C.create_string_buffer(512)
         self._s = self._lib.ligh_scheduler_new2(provider._p, device, max_pods, max_adapters, max_batch,
                                                 flush_size, batch_window_us, refresh_interval_ms, seed,
-                                                int(busy_poll), caller_spin_us, err, 512)
+                                                int(busy_poll), caller_spin_us, int(use_doorbell), err, 512)
         if not self._s:
             raise HostSchedulerError(err.value.decode("utf-8", "replace"))
 

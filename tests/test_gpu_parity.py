@@ -493,3 +493,40 @@ def test_batch_queue_graph_replay_matches_single_batches(engine):
                                        [d_out[0].data_ptr(), d_out[1].data_ptr()], stream.cuda_stream)
     stream.synchronize()
     assert np.array_equal(d_out[1].cpu().numpy().view(PICK_DTYPE), engine.schedule_batch(ep3, 4, host[1]))
+
+
+def test_doorbell_stream_matches_batch_path(oracle):
+    """K3: micro-batches through the persistent doorbell kernel give exactly the results of
+    lig_schedule_batch, across snapshot refreshes, for sizes 1..capacity; close/open cycles."""
+    e = Engine(0, max_pods=512, max_adapters=64, max_batch=8192)
+    try:
+        snap = WL.make_snapshot(300, 24, seed=51)
+        snap2 = WL.make_snapshot(300, 24, seed=52)
+        reqs = WL.make_requests(4096, 24, seed=53)
+        e.upload_snapshot(1, snap.packed)
+        want_full = e.schedule_batch(1, 99, reqs)
+        e.stream_open()
+        e.stream_open()                                   # idempotent
+        for n in (1, 2, 31, 256, 257, 1000, 4096):
+            got = e.stream_submit(1, 99, np.ascontiguousarray(reqs[:n]))
+            assert np.array_equal(got, want_full[:n]), n
+        assert len(e.stream_submit(1, 99, reqs[:0])) == 0
+        with pytest.raises(N.LigError):
+            e.stream_submit(1, 99, WL.make_requests(4097, 24))
+        # a snapshot refresh while the kernel is resident: the new tables must be seen (L2 reads)
+        e.upload_snapshot(2, snap2.packed)
+        got2 = e.stream_submit(2, 7, reqs)
+        e.stream_close()
+        assert np.array_equal(got2, e.schedule_batch(2, 7, reqs))
+        want_o, _ = oracle.Pool(snap2.pod_records()).schedule_batch(snap2.adapter_names(), WL.UNKNOWN_MODEL, reqs, 7)
+        assert np.array_equal(got2, want_o)
+        with pytest.raises(N.LigError):                   # closed
+            e.stream_submit(2, 7, reqs)
+        e.stream_open()                                   # reopen: tickets restart
+        assert np.array_equal(e.stream_submit(2, 7, reqs), got2)
+        for i in range(300):                              # many tickets
+            assert np.array_equal(e.stream_submit(2, i, np.ascontiguousarray(reqs[:8])), e.schedule_batch(2, i, np.ascontiguousarray(reqs[:8])))
+        e.stream_close()
+        e.stream_close()
+    finally:
+        e.close()
