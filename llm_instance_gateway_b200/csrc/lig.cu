@@ -774,7 +774,9 @@ int lig_schedule_batches_device(lig_ctx* c, uint64_t epoch, uint64_t seed,
   // queue streams round-robin and join back, so the tail of batch b overlaps the head of b+1
   // while everything stays ordered with respect to `stream`.
   const int ns = (n_batches > 1) ? c->queue_streams : 1;
-  const int pd = c->prefetch_distance;
+  // L2 prefetch of the next batch only pays while a few batches fit the 126 MB L2 together;
+  // beyond that the prefetched lines are evicted before use and every descriptor is read twice
+  const int pd = ((size_t)R * sizeof(lig_req) <= ((size_t)32 << 20)) ? c->prefetch_distance : 0;
   if (n_batches >= 2 && R > 0 && R <= c->merge_max_requests) {
     // small batches: one launch for up to 65535 of them
     const uint2* cls = reinterpret_cast<const uint2*>(s->d_cls);
