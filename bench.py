@@ -469,10 +469,20 @@ def main():
             nthreads = oracle.hardware_threads()
             v, sample = cpu_reference_rate(snap, host_batches[0], 123, nthreads, args.cpu_seconds)
             v1, sample1 = cpu_reference_rate(snap, host_batches[0], 123, 1, min(args.cpu_seconds, 3.0))
+            from oracle import binding as _ob
+            pk = snap.packed
+            n_opt = min(R, 1 << 19)
+            t0 = time.perf_counter()
+            _ob.soa_schedule_batch(pk.P, pk.A, pk.kv, pk.q, pk.n_active, pk.max_active, pk.bitmap,
+                                   np.ascontiguousarray(host_batches[0][:n_opt]), 123, False, nthreads)
+            v_opt = n_opt / (time.perf_counter() - t0)
             line["cpu_baseline"] = {
                 "value": v, "unit": UNIT, "cores": nthreads, "kind": "port",
                 "sample": f"first {sample} requests of batch 0 of the same workload",
                 "single_thread": {"value": v1, "sample": sample1},
+                "optimised_cpu": {"value": v_opt, "cores": nthreads, "sample": n_opt,
+                                  "note": "fairness datapoint (oracle/lig_oracle_soa.c): same per-request tree "
+                                          "walk on columns + adapter bitmaps + mask words, no allocation"},
                 "cgroup_cpu_quota_cores": cpu_quota(),
                 "note": "C restatement of the Go scheduler with the reference's data structures "
                         "(Go toolchain absent from the image)"}

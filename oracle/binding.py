@@ -55,6 +55,8 @@ def load() -> C.CDLL:
     lib.lig_oracle_filter_error_leaf.argtypes = [vp, vp, C.POINTER(i32)]
     lib.lig_oracle_schedule.argtypes = [vp, C.c_char_p, i32, u64, u64, C.POINTER(C.c_int32), C.POINTER(i32)]
     lib.lig_oracle_schedule_batch.argtypes = [vp, cpp, i32, C.c_char_p, vp, i32, u64, vp, vp, i32]
+    lib.lig_oracle_soa_schedule_batch.argtypes = [i32, i32, vp, vp, vp, vp, vp, dbl, i64, i64, vp, i32, u64,
+                                                  vp, vp, i32]
     lib.lig_oracle_splitmix64_next.argtypes = [C.POINTER(u64)]
     lib.lig_oracle_splitmix64_next.restype = u64
     lib.lig_oracle_int31n.argtypes = [C.POINTER(u64), C.c_int32]
@@ -134,6 +136,25 @@ class Pool:
             masks.ctypes.data if (masks is not None and masks.size) else None, nthreads)
         assert rc == 0
         return out, masks
+
+
+def soa_schedule_batch(P, A, kv, q, n_active, max_active, bitmap, reqs, seed, want_masks=False,
+                       nthreads=1, thresholds=(0.8, 5, 50)):
+    """The optimised-CPU variant on the packed columns (numpy arrays as in PackedSnapshot)."""
+    lib = load()
+    assert reqs.dtype == REQ_DTYPE and reqs.flags.c_contiguous
+    R = int(reqs.shape[0])
+    out = np.zeros(R, dtype=PICK_DTYPE)
+    W = (P + 31) // 32
+    masks = np.zeros((R, W), dtype=np.uint32) if want_masks else None
+    ptr = lambda a: a.ctypes.data if a is not None and a.size else None
+    rc = lib.lig_oracle_soa_schedule_batch(
+        P, A, ptr(np.ascontiguousarray(kv, dtype=np.float64)), ptr(np.ascontiguousarray(q, dtype=np.int32)),
+        ptr(np.ascontiguousarray(n_active, dtype=np.uint16)), ptr(np.ascontiguousarray(max_active, dtype=np.uint16)),
+        ptr(np.ascontiguousarray(bitmap, dtype=np.uint32)), thresholds[0], thresholds[1], thresholds[2],
+        ptr(reqs), R, seed, ptr(out), ptr(masks), nthreads)
+    assert rc == 0
+    return out, masks
 
 
 def set_thresholds(kv=0.8, qcrit=5, qlora=50) -> None:

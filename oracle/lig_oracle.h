@@ -86,6 +86,16 @@ int lig_oracle_schedule_batch(const lig_oracle_pool*, const char* const* adapter
                               const lig_oracle_req* reqs, int R, uint64_t seed,
                               lig_oracle_pick* out, uint32_t* masks, int nthreads);
 
+/* "Optimised CPU" fairness datapoint (lig_oracle_soa.c): the same per-request tree walk on the
+ * GPU's data layout (columns + adapter-major bitmap + mask words), no allocation per request.
+ * Column meanings as in include/lig.h; thresholds passed explicitly. */
+int lig_oracle_soa_schedule_batch(int P, int A, const double* kv, const int32_t* q,
+                                  const uint16_t* n_active, const uint16_t* max_active,
+                                  const uint32_t* bitmap_adapter_major, double kv_cache_threshold,
+                                  int64_t queue_threshold_critical, int64_t queueing_threshold_lora,
+                                  const lig_oracle_req* reqs, int R, uint64_t seed,
+                                  lig_oracle_pick* out, uint32_t* masks, int nthreads);
+
 /* The pick primitives, exposed for known-answer tests. */
 uint64_t lig_oracle_splitmix64_next(uint64_t* state);
 int32_t  lig_oracle_int31n(uint64_t* state, int32_t n);

@@ -127,3 +127,44 @@ def test_no_fma_in_kv_threshold(oracle):
         assert idx == want
         found += 1
     assert found == 2000
+
+
+def test_soa_variant_equals_structure_preserving_port(oracle):
+    """The optimised-CPU datapoint (columns + bitmaps + mask words) against the reference-shaped
+    port, on the synthetic configs and on adversarial pools (status, n, pick and survivor mask)."""
+    import math
+    from llm_instance_gateway_b200 import workload as WL
+    from llm_instance_gateway_b200.packer import REQ_DTYPE, pack_pod_metrics
+    from llm_instance_gateway_b200.backend import Metrics, Pod, PodMetrics
+    for P, A, R in [(8, 4, 2000), (64, 32, 1024), (300, 24, 3000), (1, 0, 64), (65, 3, 500)]:
+        snap = WL.make_snapshot(P, A, seed=P + A)
+        reqs = WL.make_requests(R, A, seed=R)
+        reqs["adapter_id"][::17] = -3
+        p = snap.packed
+        want, wm = oracle.Pool(snap.pod_records()).schedule_batch(snap.adapter_names(), WL.UNKNOWN_MODEL, reqs, 11, True)
+        got, gm = oracle.soa_schedule_batch(P, A, p.kv, p.q, p.n_active, p.max_active, p.bitmap, reqs, 11, True, 3)
+        assert np.array_equal(got, want) and np.array_equal(gm, wm), (P, A)
+    rng = np.random.default_rng(8)
+    special = [0.0, -0.0, 0.8, 0.8000000000000002, 1.0, math.inf, -math.inf, math.nan, 5e-324, -0.25]
+    for it in range(60):
+        P = int(rng.integers(0, 80))
+        pods = [PodMetrics(Pod(f"pod-{i}", f"address-{i}"),
+                           Metrics(WaitingQueueSize=int(rng.choice([0, 5, 6, 49, 50, -1, 2**31 - 1, -(2**31), int(rng.integers(0, 70))])),
+                                   KVCacheUsagePercent=float(rng.choice(special)) if rng.random() < 0.3 else float(np.round(rng.random(), 2)),
+                                   MaxActiveModels=int(rng.integers(0, 4)),
+                                   ActiveModels={a: 1 for a in rng.choice(["a0", "a1", "a2"], size=int(rng.integers(0, 3)), replace=False)}))
+                for i in range(P)]
+        p = pack_pod_metrics(pods)
+        names = [None] * p.A
+        for k, v in p.adapter_ids.items():
+            names[v] = k
+        reqs = np.zeros(2 * (p.A + 2), dtype=REQ_DTYPE)
+        reqs["adapter_id"] = list(range(-1, p.A + 1)) * 2
+        reqs["flags"] = [0] * (p.A + 2) + [1] * (p.A + 2)
+        reqs["rand_key"] = rng.integers(0, 1 << 64, len(reqs), dtype=np.uint64)
+        records = [dict(name=x.Pod.Name, address=x.Pod.Address, waiting_queue_size=x.Metrics.WaitingQueueSize,
+                        kv_cache_usage_percent=x.Metrics.KVCacheUsagePercent, max_active_models=x.Metrics.MaxActiveModels,
+                        active_models=list(x.Metrics.ActiveModels)) for x in pods]
+        want, wm = oracle.Pool(records).schedule_batch(names, "zz-unknown", reqs, it, True)
+        got, gm = oracle.soa_schedule_batch(p.P, p.A, p.kv, p.q, p.n_active, p.max_active, p.bitmap, reqs, it, True, 1)
+        assert np.array_equal(got, want) and np.array_equal(gm, wm), it
