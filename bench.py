@@ -452,7 +452,9 @@ def main():
             "gpu_launches": int(launches_per_region),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": committed_traffic(args.workload),
-                         "kernel": "lig_pick_stream_kernel", "algorithmic_bytes_per_launch": alg_bytes,
+                         "kernel": ("lig_pick_queue_kernel" if (R <= (1 << 17) and K >= 2 and launches_per_region < K)
+                                    else "lig_pick_stream_kernel"),
+                         "algorithmic_bytes_per_launch": alg_bytes,
                          "launch_us": launch_s * 1e6, "peak_source": peak_src},
             "clocks": clocks,
             "snapshot_build_us": snapshot_build_us,
