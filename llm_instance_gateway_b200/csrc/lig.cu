@@ -212,14 +212,14 @@ int launch_class_build(lig_ctx* c, Slot& s, cudaStream_t stream) {
   const size_t smem = build_fixed_bytes(W) + (staged ? staged_bytes(W) : 0);
   // every CTA repeats the shared stages, so no more CTAs than needed to give each warp a couple
   // of classes, and never more than one per SM
-  int grid = (n_classes + 2 * kWarpsPerCta - 1) / (2 * kWarpsPerCta);
+  int grid = (n_classes + 2 * kBuildWarps - 1) / (2 * kBuildWarps);
   if (grid > c->sm_count) grid = c->sm_count;
   if (grid < 1) grid = 1;
   const int stride = s.P > 0 ? s.P : 1;
   if (staged) {
-    lig_class_build_kernel<true><<<grid, kCtaThreads, smem, stream>>>(v, thr_of(c), s.d_cls, s.d_lists, stride);
+    lig_class_build_kernel<true><<<grid, kBuildThreads, smem, stream>>>(v, thr_of(c), s.d_cls, s.d_lists, stride);
   } else {
-    lig_class_build_kernel<false><<<grid, kCtaThreads, smem, stream>>>(v, thr_of(c), s.d_cls, s.d_lists, stride);
+    lig_class_build_kernel<false><<<grid, kBuildThreads, smem, stream>>>(v, thr_of(c), s.d_cls, s.d_lists, stride);
   }
   CUDA_TRY(cudaGetLastError());
   c->launches++;

@@ -379,21 +379,24 @@ __device__ __forceinline__ const uint32_t* stage_adapter_row(const SnapView& s, 
 //
 // Most of the tree does not depend on the adapter: the low-queue set, the
 // "has room" set, the sheddable-capacity set and the least-queuing stage that follows them are
-// the same for every class.  Each CTA therefore first walks those shared stages once with all 8
+// the same for every class.  Each CTA therefore first walks those shared stages once with all its
 // warps (dense, pod-parallel, ballot words), and a class then only costs one AND of its bitmap
 // row with a shared mask; only classes whose adapter actually intersects the mask run their own
 // range filters, on the (sparse) set bits.  Classes that do not intersect share one of two
 // default survivor lists.  lig_scan_kernel keeps the plain per-request walk (tree_eval_warp), so
 // the GPU holds two independent formulations of the tree (the parity tests check both).
 
+constexpr int kBuildWarps = 16;   // the class build runs 512-thread CTAs, at most one per SM
+constexpr int kBuildThreads = kBuildWarps * 32;
+
 struct BuildShared {        // block-wide scalars of the shared stages (shared memory)
   uint32_t n_shed;          // |S|, S = {q <= q_crit && kv <= kv_thr}              scheduler.go:74-79
   uint32_t crit_mode;       // 0: low-queue set non-empty; 1: empty (all pods go to queueLoRAAndKV)
   uint32_t rc_n, rc_status; // default result of critical classes
   uint32_t rs_n, rs_status; // default result of sheddable classes
-  uint32_t red_u[kWarpsPerCta];
-  int red_i[2 * kWarpsPerCta];
-  double red_d[2 * kWarpsPerCta];
+  uint32_t red_u[kBuildWarps];
+  int red_i[2 * kBuildWarps];
+  double red_d[2 * kBuildWarps];
 };
 
 __device__ __forceinline__ uint32_t blk_sum(uint32_t warp_value, BuildShared* sh, int warp, int lane) {
@@ -402,7 +405,7 @@ __device__ __forceinline__ uint32_t blk_sum(uint32_t warp_value, BuildShared* sh
   __syncthreads();
   uint32_t t = 0;
 #pragma unroll
-  for (int i = 0; i < kWarpsPerCta; ++i) t += sh->red_u[i];
+  for (int i = 0; i < kBuildWarps; ++i) t += sh->red_u[i];
   return t;
 }
 
@@ -411,7 +414,7 @@ template <class Pred>
 __device__ __forceinline__ uint32_t blk_pred_pass(uint32_t* out, const uint32_t* in, int P, int W,
                                                   BuildShared* sh, int warp, int lane, Pred pred) {
   uint32_t cnt = 0;
-  for (int w = warp; w < W; w += kWarpsPerCta) {
+  for (int w = warp; w < W; w += kBuildWarps) {
     const int p = w * 32 + lane;
     const bool member = in ? ((in[w] >> lane) & 1u) : (p < P);
     const bool keep = member && pred(p);
@@ -428,7 +431,7 @@ __device__ __forceinline__ uint32_t blk_least_queuing(const Fields& f, uint32_t*
                                                       BuildShared* sh, int warp, int lane) {
   if (n == 0) return 0;
   int mn = 0x7fffffff, mx = 0;
-  for (int w = warp; w < W; w += kWarpsPerCta) {
+  for (int w = warp; w < W; w += kBuildWarps) {
     if ((X[w] >> lane) & 1u) {
       const int v = ld_q<kStaged>(f, w * 32 + lane);
       mn = min(mn, v);
@@ -438,17 +441,17 @@ __device__ __forceinline__ uint32_t blk_least_queuing(const Fields& f, uint32_t*
   mn = __reduce_min_sync(kFull, mn);
   mx = __reduce_max_sync(kFull, mx);
   __syncthreads();
-  if (lane == 0) { sh->red_i[warp] = mn; sh->red_i[kWarpsPerCta + warp] = mx; }
+  if (lane == 0) { sh->red_i[warp] = mn; sh->red_i[kBuildWarps + warp] = mx; }
   __syncthreads();
 #pragma unroll
-  for (int i = 0; i < kWarpsPerCta; ++i) {
+  for (int i = 0; i < kBuildWarps; ++i) {
     mn = min(mn, sh->red_i[i]);
-    mx = max(mx, sh->red_i[kWarpsPerCta + i]);
+    mx = max(mx, sh->red_i[kBuildWarps + i]);
   }
   const uint32_t range = (uint32_t)mx - (uint32_t)mn;   // see stage_least_queuing
   const long long thr = (long long)mn + (long long)(range / n);
   uint32_t cnt = 0;
-  for (int w = warp; w < W; w += kWarpsPerCta) {
+  for (int w = warp; w < W; w += kBuildWarps) {
     const uint32_t word = X[w];
     bool keep = false;
     if ((word >> lane) & 1u) {
@@ -469,7 +472,7 @@ __device__ __forceinline__ uint32_t blk_least_kv(const Fields& f, uint32_t* X, i
                                                  BuildShared* sh, int warp, int lane) {
   if (n == 0) return 0;
   double mn = 1.7976931348623157e308, mx = 0.0;
-  for (int w = warp; w < W; w += kWarpsPerCta) {
+  for (int w = warp; w < W; w += kBuildWarps) {
     if ((X[w] >> lane) & 1u) {
       const double v = ld_kv<kStaged>(f, w * 32 + lane);
       if (v <= mn) mn = v;
@@ -484,17 +487,17 @@ __device__ __forceinline__ uint32_t blk_least_kv(const Fields& f, uint32_t* X, i
     if (o > mx) mx = o;
   }
   __syncthreads();
-  if (lane == 0) { sh->red_d[warp] = mn; sh->red_d[kWarpsPerCta + warp] = mx; }
+  if (lane == 0) { sh->red_d[warp] = mn; sh->red_d[kBuildWarps + warp] = mx; }
   __syncthreads();
 #pragma unroll
-  for (int i = 0; i < kWarpsPerCta; ++i) {
-    const double a = sh->red_d[i], b = sh->red_d[kWarpsPerCta + i];
+  for (int i = 0; i < kBuildWarps; ++i) {
+    const double a = sh->red_d[i], b = sh->red_d[kBuildWarps + i];
     if (a < mn) mn = a;
     if (b > mx) mx = b;
   }
   const double thr = __dadd_rn(mn, __ddiv_rn(__dsub_rn(mx, mn), (double)n));
   uint32_t cnt = 0;
-  for (int w = warp; w < W; w += kWarpsPerCta) {
+  for (int w = warp; w < W; w += kBuildWarps) {
     const uint32_t word = X[w];
     bool keep = false;
     if ((word >> lane) & 1u) {
@@ -612,10 +615,10 @@ __device__ __forceinline__ void compact_mask_to_list(const uint32_t* X, int W, i
 }
 
 // Shared-memory carve-up of the class build:
-//   [ BuildShared ][ 6 block masks x W ][ per-warp scratch kWarpsPerCta x W ][ staged columns ]
+//   [ BuildShared ][ 7 block masks x W ][ per-warp scratch kBuildWarps x W ][ staged columns ]
 __host__ __device__ inline size_t build_fixed_bytes(int W) {
   const size_t b = ((sizeof(BuildShared) + 15) & ~(size_t)15) +
-                   (size_t)(6 + kWarpsPerCta) * (size_t)W * sizeof(uint32_t);
+                   (size_t)(7 + kBuildWarps) * (size_t)W * sizeof(uint32_t);
   return (b + 15) & ~(size_t)15;   // the staged columns behind it are written with 16-byte stores
 }
 
@@ -637,7 +640,7 @@ __device__ __forceinline__ ClassEntry make_entry(uint32_t n, uint32_t status, ui
 }
 
 template <bool kStaged>
-__global__ void __launch_bounds__(kCtaThreads)
+__global__ void __launch_bounds__(kBuildThreads)
 lig_class_build_kernel(SnapView s, Thr thr, ClassEntry* __restrict__ cls,
                        uint16_t* __restrict__ lists, int list_stride) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -651,7 +654,8 @@ lig_class_build_kernel(SnapView s, Thr thr, ClassEntry* __restrict__ cls,
   uint32_t* SB = masks + 3 * W;        // sheddable: (least-queuing set of S) & ~room
   uint32_t* SZ = masks + 4 * W;        // sheddable: (least-queuing set of S) & room
   uint32_t* TMP = masks + 5 * W;
-  uint32_t* X = masks + (size_t)(6 + warp) * W;   // per-warp scratch
+  uint32_t* SHED = masks + 6 * W;      // q <= q_crit && kv <= kv_thr                 filter.go:183-187
+  uint32_t* X = masks + (size_t)(7 + warp) * W;   // per-warp scratch
   Fields f{s.kv, s.q, s.n_active, s.max_active};
   if constexpr (kStaged) {
     f = stage_fields(s, smem + build_fixed_bytes(W));
@@ -662,30 +666,45 @@ lig_class_build_kernel(SnapView s, Thr thr, ClassEntry* __restrict__ cls,
   const uint32_t rs_row = rc_row + (uint32_t)list_stride;
 
   if (P == 0) {   // critical: predicate node errs on an empty pool -> sheddable branch -> drop
-    for (int c = blockIdx.x * kCtaThreads + threadIdx.x; c < n_classes; c += gridDim.x * kCtaThreads)
+    for (int c = blockIdx.x * kBuildThreads + threadIdx.x; c < n_classes; c += gridDim.x * kBuildThreads)
       cls[c] = make_entry(0u, (uint32_t)LIG_DROP, kRowOwn);
     return;
   }
 
-  // ---- shared stages (every CTA, all 8 warps) -------------------------------------------------
+  // ---- shared stages (every CTA, all its warps) -----------------------------------------------
   auto ldq = [&](int p) { return (long long)ld_q<kStaged>(f, p); };
-  blk_pred_pass(M_room, nullptr, P, W, sh, warp, lane, [&](int p) { return has_room<kStaged>(f, p); });
-  // critical side: "low queueing filter"                                  scheduler.go:58-60
-  const uint32_t n_low = blk_pred_pass(CB, nullptr, P, W, sh, warp, lane,
-                                       [&](int p) { return ldq(p) < thr.q_lora; });
+  // one pass over the pods for the three request-independent predicate sets
+  uint32_t n_low = 0, n_shed_w = 0;
+  for (int w = warp; w < W; w += kBuildWarps) {
+    const int p = w * 32 + lane;
+    bool room = false, low = false, shed = false;
+    if (p < P) {
+      const long long qq = ldq(p);
+      room = has_room<kStaged>(f, p);                                     // filter.go:175-177
+      low = qq < thr.q_lora;                                              // scheduler.go:58-60
+      shed = qq <= thr.q_crit && ld_kv<kStaged>(f, p) <= thr.kv_thr;      // scheduler.go:74-79
+    }
+    const uint32_t wr = __ballot_sync(kFull, room), wl = __ballot_sync(kFull, low),
+                   ws = __ballot_sync(kFull, shed);
+    if (lane == 0) { M_room[w] = wr; CB[w] = wl; SHED[w] = ws; }
+    n_low += __popc(wl);
+    n_shed_w += __popc(ws);
+  }
+  n_low = blk_sum(n_low, sh, warp, lane);
+  const uint32_t n_shed = blk_sum(n_shed_w, sh, warp, lane);
   uint32_t rc_n, rc_status;
   if (n_low > 0) {
     // default (adapter active in none of the low-queue pods): "can accept LoRA Adapter" on the
     // low-queue set, falling back to that set, then queueAndKVCacheFilter   scheduler.go:65-69,49-56
     uint32_t nc = 0;
-    for (int w = warp; w < W; w += kWarpsPerCta) {
+    for (int w = warp; w < W; w += kBuildWarps) {
       const uint32_t t = CB[w] & M_room[w];
       if (lane == 0) TMP[w] = t;
       nc += __popc(t);
     }
     nc = blk_sum(nc, sh, warp, lane);
     if (nc == 0) {
-      for (int w = threadIdx.x; w < W; w += kCtaThreads) TMP[w] = CB[w];
+      for (int w = threadIdx.x; w < W; w += kBuildThreads) TMP[w] = CB[w];
       nc = n_low;
     }
     __syncthreads();
@@ -699,14 +718,14 @@ lig_class_build_kernel(SnapView s, Thr thr, ClassEntry* __restrict__ cls,
     uint32_t ny = blk_pred_pass(TMP, nullptr, P, W, sh, warp, lane, [&](int) { return true; });
     ny = blk_least_queuing<kStaged>(f, TMP, W, ny, sh, warp, lane);
     uint32_t nz = 0;
-    for (int w = warp; w < W; w += kWarpsPerCta) {
+    for (int w = warp; w < W; w += kBuildWarps) {
       const uint32_t y = TMP[w], r = M_room[w];
       if (lane == 0) { CZ[w] = y & r; CB[w] = y & ~r; }
       nz += __popc(y & r);
     }
     nz = blk_sum(nz, sh, warp, lane);
     if (nz > 0) {
-      for (int w = threadIdx.x; w < W; w += kCtaThreads) TMP[w] = CZ[w];
+      for (int w = threadIdx.x; w < W; w += kBuildThreads) TMP[w] = CZ[w];
       ny = nz;
     }
     __syncthreads();
@@ -717,20 +736,19 @@ lig_class_build_kernel(SnapView s, Thr thr, ClassEntry* __restrict__ cls,
   }
   // sheddable side: "has capacity for sheddable requests"                 scheduler.go:74-79
   uint32_t rs_n = 0, rs_status = LIG_DROP;
-  const uint32_t n_shed = blk_pred_pass(TMP, nullptr, P, W, sh, warp, lane, [&](int p) {
-    return ldq(p) <= thr.q_crit && ld_kv<kStaged>(f, p) <= thr.kv_thr;
-  });
+  for (int w = threadIdx.x; w < W; w += kBuildThreads) TMP[w] = SHED[w];
+  __syncthreads();
   if (n_shed > 0) {
     uint32_t ny = blk_least_queuing<kStaged>(f, TMP, W, n_shed, sh, warp, lane);
     uint32_t nz = 0;
-    for (int w = warp; w < W; w += kWarpsPerCta) {
+    for (int w = warp; w < W; w += kBuildWarps) {
       const uint32_t y = TMP[w], r = M_room[w];
       if (lane == 0) { SZ[w] = y & r; SB[w] = y & ~r; }
       nz += __popc(y & r);
     }
     nz = blk_sum(nz, sh, warp, lane);
     if (nz > 0) {
-      for (int w = threadIdx.x; w < W; w += kCtaThreads) TMP[w] = SZ[w];
+      for (int w = threadIdx.x; w < W; w += kBuildThreads) TMP[w] = SZ[w];
       ny = nz;
     }
     __syncthreads();
@@ -741,7 +759,7 @@ lig_class_build_kernel(SnapView s, Thr thr, ClassEntry* __restrict__ cls,
   __syncthreads();
 
   // ---- per class (one warp each): AND the adapter row with the shared mask --------------------
-  for (int c = blockIdx.x * kWarpsPerCta + warp; c < n_classes; c += gridDim.x * kWarpsPerCta) {
+  for (int c = blockIdx.x * kBuildWarps + warp; c < n_classes; c += gridDim.x * kBuildWarps) {
     const bool critical = c >= A + 1;
     const int a = critical ? c - (A + 1) : c;
     const uint32_t* row = a < A ? s.bitmap + (size_t)a * W : nullptr;
