@@ -51,6 +51,16 @@ int fail(int code, const char* fmt, ...) {
 
 inline int words_for(int P) { return (P + 31) / 32; }
 
+// Run STMT with the compile-time constant kPpt bound to the run-time requests-per-thread knob.
+#define LIG_DISPATCH_PPT(ppt, STMT)                           \
+  switch (ppt) {                                              \
+    case 1:  { constexpr int kPpt = 1;  STMT; } break;        \
+    case 2:  { constexpr int kPpt = 2;  STMT; } break;        \
+    case 8:  { constexpr int kPpt = 8;  STMT; } break;        \
+    case 16: { constexpr int kPpt = 16; STMT; } break;        \
+    default: { constexpr int kPpt = 4;  STMT; } break;        \
+  }
+
 struct Layout {  // offsets into the packed blob
   size_t kv, q, na, ma, bitmap, total;
 };
@@ -260,14 +270,10 @@ int launch_pick(lig_ctx* c, const Slot& s, uint64_t seed, const lig_req* d_reqs,
   const int grid = (R + per_cta - 1) / per_cta;
   overlap_prev = overlap_prev && c->use_pdl;
   const int4* pf = reinterpret_cast<const int4*>(prefetch_reqs);
-  cudaError_t e;
-  switch (c->pick_per_thread) {
-    case 1: e = launch_pick_variant<1>(grid, stream, overlap_prev, in, out, R, cls, s.d_lists, stride, s.A, seed, pf); break;
-    case 2: e = launch_pick_variant<2>(grid, stream, overlap_prev, in, out, R, cls, s.d_lists, stride, s.A, seed, pf); break;
-    case 8: e = launch_pick_variant<8>(grid, stream, overlap_prev, in, out, R, cls, s.d_lists, stride, s.A, seed, pf); break;
-    case 16: e = launch_pick_variant<16>(grid, stream, overlap_prev, in, out, R, cls, s.d_lists, stride, s.A, seed, pf); break;
-    default: e = launch_pick_variant<4>(grid, stream, overlap_prev, in, out, R, cls, s.d_lists, stride, s.A, seed, pf); break;
-  }
+  cudaError_t e = cudaSuccess;
+  LIG_DISPATCH_PPT(c->pick_per_thread,
+                   e = launch_pick_variant<kPpt>(grid, stream, overlap_prev, in, out, R, cls, s.d_lists,
+                                                 stride, s.A, seed, pf));
   CUDA_TRY(e);
   c->launches++;
   return 0;
@@ -338,14 +344,8 @@ int build_queue_graph(const Slot& s, QueueGraph* g, int n_batches) {
   kp.blockDim = dim3(1);
   kp.kernelParams = seed_args;
   CUDA_TRY(cudaGraphAddKernelNode(&g->seed_node, g->graph, nullptr, 0, &kp));
-  void* fn;
-  switch (g->ppt) {
-    case 1: fn = pick_kernel_ptr<1>(); break;
-    case 2: fn = pick_kernel_ptr<2>(); break;
-    case 8: fn = pick_kernel_ptr<8>(); break;
-    case 16: fn = pick_kernel_ptr<16>(); break;
-    default: fn = pick_kernel_ptr<4>(); break;
-  }
+  void* fn = nullptr;
+  LIG_DISPATCH_PPT(g->ppt, fn = pick_kernel_ptr<kPpt>());
   const uint2* cls = reinterpret_cast<const uint2*>(s.d_cls);
   const uint16_t* lists = s.d_lists;
   int stride = s.P > 0 ? s.P : 1;
@@ -794,13 +794,9 @@ int lig_schedule_batches_device(lig_ctx* c, uint64_t epoch, uint64_t seed,
                                cudaMemcpyHostToDevice, st));
       CUDA_TRY(cudaEventRecord(c->items_free[slot], st));
       const dim3 grid((unsigned)((R + per_cta - 1) / per_cta), (unsigned)n);
-      switch (c->pick_per_thread) {
-        case 1: lig_pick_queue_kernel<1><<<grid, kPickThreads, 0, st>>>(c->d_items[slot], R, cls, s->d_lists, stride, s->A); break;
-        case 2: lig_pick_queue_kernel<2><<<grid, kPickThreads, 0, st>>>(c->d_items[slot], R, cls, s->d_lists, stride, s->A); break;
-        case 8: lig_pick_queue_kernel<8><<<grid, kPickThreads, 0, st>>>(c->d_items[slot], R, cls, s->d_lists, stride, s->A); break;
-        case 16: lig_pick_queue_kernel<16><<<grid, kPickThreads, 0, st>>>(c->d_items[slot], R, cls, s->d_lists, stride, s->A); break;
-        default: lig_pick_queue_kernel<4><<<grid, kPickThreads, 0, st>>>(c->d_items[slot], R, cls, s->d_lists, stride, s->A); break;
-      }
+      LIG_DISPATCH_PPT(c->pick_per_thread,
+                       (lig_pick_queue_kernel<kPpt><<<grid, kPickThreads, 0, st>>>(
+                           c->d_items[slot], R, cls, s->d_lists, stride, s->A)));
       CUDA_TRY(cudaGetLastError());
       c->launches++;
     }
