@@ -78,34 +78,67 @@ Scheduler::~Scheduler() {
 // One pack per refresh tick replaces the per-request AllPodMetrics() of scheduler.go:114-115.
 Status Scheduler::Refresh() {
   std::lock_guard<std::mutex> rk(refresh_mu_);
+  const auto t_begin = std::chrono::steady_clock::now();
   auto pods = pmp_->AllPodMetrics();
   const int P = (int)pods.size();
+  const int W = (P + 31) / 32;
   auto snap = std::make_shared<Snapshot>();
   snap->pods.reserve(P);
   std::vector<double> kv(P);
   std::vector<int64_t> q(P), na(P), ma(P);
-  for (int p = 0; p < P; ++p) {
-    const backend::PodMetrics& pm = *pods[p];
-    snap->pods.push_back(pm.pod);
-    kv[p] = pm.metrics.KVCacheUsagePercent;
-    q[p] = pm.metrics.WaitingQueueSize;
-    na[p] = (int64_t)pm.metrics.ActiveModels.size();
-    ma[p] = pm.metrics.MaxActiveModels;
-    for (const auto& kvp : pm.metrics.ActiveModels)
-      snap->adapter_ids.emplace(kvp.first, (int)snap->adapter_ids.size());
+  if (!intern_) intern_ = std::make_shared<InternTable>();
+  bool table_changed = false;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    memo_.resize((size_t)P);
+    snap->pods.clear();
+    for (int p = 0; p < P; ++p) {
+      const backend::PodMetrics& pm = *pods[p];
+      snap->pods.push_back(pm.pod);
+      kv[p] = pm.metrics.KVCacheUsagePercent;
+      q[p] = pm.metrics.WaitingQueueSize;
+      na[p] = (int64_t)pm.metrics.ActiveModels.size();
+      ma[p] = pm.metrics.MaxActiveModels;
+      PodMemo& m = memo_[(size_t)p];
+      bool same = m.names.size() == pm.metrics.ActiveModels.size();
+      if (same) {
+        size_t k = 0;
+        for (const auto& kvp : pm.metrics.ActiveModels)     // std::map: ordered keys
+          if (m.names[k++] != kvp.first) { same = false; break; }
+      }
+      if (same) continue;
+      m.names.clear();
+      m.ids.clear();
+      for (const auto& kvp : pm.metrics.ActiveModels) {
+        auto it = intern_->find(kvp.first);
+        if (it == intern_->end()) {
+          if (!table_changed) {                              // copy on write: older snapshots keep theirs
+            intern_ = std::make_shared<InternTable>(*intern_);
+            table_changed = true;
+          }
+          it = intern_->emplace(kvp.first, (int)intern_->size()).first;
+        }
+        m.names.push_back(kvp.first);
+        m.ids.push_back(it->second);
+      }
+    }
+    if ((int)intern_->size() <= opt_.max_adapters || attempt == 1) break;
+    // the grow-only table outgrew the device capacity (adapters churned): re-intern from scratch
+    intern_ = std::make_shared<InternTable>();
+    table_changed = true;
+    memo_.clear();
   }
-  const int A = (int)snap->adapter_ids.size();
-  const int W = (P + 31) / 32;
+  const int A = (int)intern_->size();
   snap->A = A;
+  snap->adapter_ids = intern_;
   std::vector<uint32_t> bitmap((size_t)A * W, 0u);
   for (int p = 0; p < P; ++p)
-    for (const auto& kvp : pods[p]->metrics.ActiveModels)
-      bitmap[(size_t)snap->adapter_ids[kvp.first] * W + (p >> 5)] |= 1u << (p & 31);
+    for (int id : memo_[(size_t)p].ids) bitmap[(size_t)id * W + (p >> 5)] |= 1u << (p & 31);
   std::vector<int32_t> q32(P);
   std::vector<uint16_t> na16(P), ma16(P);
   if (lig_pack_pods(P, q.data(), na.data(), ma.data(), q32.data(), na16.data(), ma16.data()) != 0)
     return LigFailure("lig_pack_pods");
   snap->epoch = next_epoch_++;
+  const auto t_packed = std::chrono::steady_clock::now();
   if (lig_upload_snapshot(ctx_, snap->epoch, P, A, kv.data(), q32.data(), na16.data(), ma16.data(),
                           bitmap.data()) != 0)
     return LigFailure("lig_upload_snapshot");
@@ -113,8 +146,11 @@ Status Scheduler::Refresh() {
     std::lock_guard<std::mutex> lk(snap_mu_);
     snap_ = std::move(snap);
   }
+  const auto t_done = std::chrono::steady_clock::now();
   std::lock_guard<std::mutex> sk(stats_mu_);
   stats_.refreshes++;
+  stats_.last_pack_us = std::chrono::duration<double, std::micro>(t_packed - t_begin).count();
+  stats_.last_upload_us = std::chrono::duration<double, std::micro>(t_done - t_packed).count();
   return Status{};
 }
 
@@ -208,9 +244,10 @@ void Scheduler::Flush(std::vector<Waiter*>& batch) {
       }
       for (int i = 0; i < n; ++i) {
         const LLMRequest& r = *batch[done + i]->req;
-        auto it = snap->adapter_ids.find(r.ResolvedTargetModel);
-        // a model in no pod's ActiveModels: id A matches no pod, like a Go map miss (filter.go:170)
-        h_reqs_[i].adapter_id = it == snap->adapter_ids.end() ? snap->A : it->second;
+        auto it = snap->adapter_ids->find(r.ResolvedTargetModel);
+        // a model in no pod's ActiveModels: id A matches no pod, like a Go map miss (filter.go:170).
+        // An id interned after this snapshot was packed (>= A) is equally "in no pod" for it.
+        h_reqs_[i].adapter_id = (it == snap->adapter_ids->end() || it->second >= snap->A) ? snap->A : it->second;
         h_reqs_[i].flags = r.Critical ? LIG_REQ_CRITICAL : 0u;
         h_reqs_[i].rand_key = splitmix_next(rng_state_);
       }

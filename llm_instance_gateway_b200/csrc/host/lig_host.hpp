@@ -110,6 +110,8 @@ struct Stats {
   uint64_t max_batch = 0;      // largest batch flushed
   uint64_t refreshes = 0;      // snapshots uploaded
   uint64_t stale_retries = 0;  // batches re-resolved after LIG_ERR_STALE_EPOCH
+  double last_pack_us = 0;     // last Refresh: provider slice -> columns + bitmap (host)
+  double last_upload_us = 0;   // last Refresh: lig_upload_snapshot (H2D + class tables)
 };
 
 class Scheduler {
@@ -135,12 +137,22 @@ class Scheduler {
                              std::unique_ptr<Scheduler>*);
   Scheduler() = default;
 
+  using InternTable = std::unordered_map<std::string, int>;
   struct Snapshot {
     uint64_t epoch = 0;
     int A = 0;
-    std::unordered_map<std::string, int> adapter_ids;
+    std::shared_ptr<const InternTable> adapter_ids;   // shared between snapshots until a name is added
     std::vector<backend::Pod> pods;
   };
+  // Packer state kept between refreshes (guarded by refresh_mu_): adapter ids are stable while
+  // the table fits max_adapters, and a pod whose ActiveModels keys did not change since the last
+  // tick reuses its encoded ids (sequential string compares instead of hash lookups).
+  struct PodMemo {
+    std::vector<std::string> names;
+    std::vector<int> ids;
+  };
+  std::shared_ptr<InternTable> intern_;
+  std::vector<PodMemo> memo_;
   struct Waiter {
     const LLMRequest* req = nullptr;
     Status status;

@@ -130,6 +130,12 @@ void ligh_stats(ligh_scheduler* s, uint64_t out[5]) {
   out[4] = st.stale_retries;
 }
 
+void ligh_refresh_timing(ligh_scheduler* s, double out[2]) {
+  scheduling::Stats st = s->sched->stats();
+  out[0] = st.last_pack_us;
+  out[1] = st.last_upload_us;
+}
+
 static int pod_index(const std::vector<std::shared_ptr<const backend::PodMetrics>>& pods,
                      const backend::Pod& pod) {
   for (size_t i = 0; i < pods.size(); ++i)

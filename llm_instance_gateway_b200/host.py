@@ -24,7 +24,7 @@ EXPORTED_SYMBOLS = (
     "ligh_provider_new", "ligh_provider_free", "ligh_provider_set_pods", "ligh_scheduler_new",
     "ligh_scheduler_new2",
     "ligh_scheduler_free", "ligh_schedule", "ligh_refresh", "ligh_stats",
-    "ligh_schedule_concurrent", "ligh_stream_bench",
+    "ligh_schedule_concurrent", "ligh_stream_bench", "ligh_refresh_timing",
 )
 
 _lib = None
@@ -54,6 +54,8 @@ def load() -> C.CDLL:
     lib.ligh_refresh.argtypes = [vp, C.c_char_p, i32]
     lib.ligh_stats.argtypes = [vp, vp]
     lib.ligh_stats.restype = None
+    lib.ligh_refresh_timing.argtypes = [vp, vp]
+    lib.ligh_refresh_timing.restype = None
     lib.ligh_schedule_concurrent.argtypes = [vp, i32, i32, cpp, vp, i32, vp, vp]
     lib.ligh_stream_bench.argtypes = [vp, C.c_double, C.c_double, i32, cpp, vp, i32, u64, vp, i32,
                                       C.POINTER(i32), C.POINTER(i32)]
@@ -142,6 +144,11 @@ class HostScheduler:
         out = (C.c_uint64 * 5)()
         self._lib.ligh_stats(self._s, out)
         return dict(zip(("scheduled", "batches", "max_batch", "refreshes", "stale_retries"), map(int, out)))
+
+    def refresh_timing(self) -> dict:
+        out = (C.c_double * 2)()
+        self._lib.ligh_refresh_timing(self._s, out)
+        return {"pack_us": float(out[0]), "upload_us": float(out[1])}
 
     def schedule_concurrent(self, n_threads: int, per_thread: int, models: Sequence[str],
                             critical: Sequence[bool]):

@@ -151,3 +151,38 @@ def test_reference_load_test_shape(oracle):
     assert st["scheduled"] == len(codes) and st["batches"] < len(codes)
     s.close()
     prov.close()
+
+
+@pytest.mark.gpu
+def test_adapter_churn_across_refreshes(oracle):
+    """The packer keeps adapter ids stable between refresh ticks and re-interns from scratch when
+    churn outgrows max_adapters; picks must follow every snapshot exactly."""
+    rng = np.random.default_rng(3)
+    prov = H.HostProvider([])
+    s = H.HostScheduler(prov, max_pods=64, max_adapters=12, max_batch=256)
+    universe = [f"lora-{i}" for i in range(40)]
+    for tick in range(12):
+        live = list(rng.choice(universe, size=8, replace=False))          # 8 of 40 names alive per tick
+        pods = [PodMetrics(Pod(f"pod-{i}", f"address-{i}"),
+                           Metrics(WaitingQueueSize=int(rng.integers(0, 60)), KVCacheUsagePercent=float(np.round(rng.random(), 2)),
+                                   MaxActiveModels=int(rng.integers(0, 4)),
+                                   ActiveModels={a: 1 for a in rng.choice(live, size=int(rng.integers(0, 4)), replace=False)}))
+                for i in range(int(rng.integers(1, 40)))]
+        prov.set_pods(pods)
+        s.Refresh()
+        pool = oracle.Pool([dict(name=p.Pod.Name, address=p.Pod.Address, waiting_queue_size=p.Metrics.WaitingQueueSize,
+                                 kv_cache_usage_percent=p.Metrics.KVCacheUsagePercent, max_active_models=p.Metrics.MaxActiveModels,
+                                 active_models=list(p.Metrics.ActiveModels)) for p in pods])
+        for model in live[:4] + ["never-loaded", universe[0]]:
+            for crit in (False, True):
+                rc, survivors = pool.filter(model, crit)
+                code, pod, _ = s.Schedule(model, model, crit)
+                if rc == oracle.LIGO_OK:
+                    assert code == H.GRPC_OK and int(pod.Name.split("-")[1]) in survivors, (tick, model, crit)
+                elif rc == oracle.LIGO_DROP:
+                    assert code == H.GRPC_RESOURCE_EXHAUSTED
+                else:
+                    assert code == H.GRPC_UNKNOWN
+    assert s.stats()["refreshes"] == 13
+    s.close()
+    prov.close()
