@@ -57,6 +57,8 @@ def parse_args():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: every GPU schedules R requests per step (default); strong: the "
                          "workload's R requests are sharded contiguously over the GPUs")
+    ap.add_argument("--ring", type=int, default=0,
+                    help="number of distinct resident batches cycled (default: enough for 2x the L2)")
     ap.add_argument("--timed-only", action="store_true",
                     help="run only warm-up + the K-step timed region (for ncu launch lists)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -298,6 +300,8 @@ def main():
     # --- resident request batches: more distinct bytes than L2 so no step re-reads a cached batch
     nb = max(4, -(-2 * L2_BYTES // (R * 24)))
     nb = min(nb, 64)
+    if args.ring > 0:
+        nb = args.ring
     host_batches = [WL.make_requests(R, A, seed=WL.REQUEST_SEED + 1000 * rank + b) for b in range(min(nb, 8))]
     d_reqs, d_out = [], []
     for b in range(nb):
