@@ -136,13 +136,6 @@ void ligh_refresh_timing(ligh_scheduler* s, double out[2]) {
   out[1] = st.last_upload_us;
 }
 
-static int pod_index(const std::vector<std::shared_ptr<const backend::PodMetrics>>& pods,
-                     const backend::Pod& pod) {
-  for (size_t i = 0; i < pods.size(); ++i)
-    if (pods[i]->pod.Name == pod.Name && pods[i]->pod.Address == pod.Address) return (int)i;
-  return -1;
-}
-
 int ligh_schedule_concurrent(ligh_scheduler* s, int n_threads, int per_thread,
                              const char* const* models, const int* critical, int n_models,
                              int* out_codes, int* out_pod) {
@@ -172,7 +165,6 @@ int ligh_schedule_concurrent(ligh_scheduler* s, int n_threads, int per_thread,
     });
   }
   for (auto& x : th) x.join();
-  (void)pod_index;
   return 0;
 }
 

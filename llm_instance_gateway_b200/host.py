@@ -127,7 +127,7 @@ class HostScheduler:
             self._s = None
 
     def Schedule(self, model: str, resolved: str, critical: bool) -> Tuple[int, Optional[Pod], str]:  # noqa: N802
-        name, addr, err = (C.create_string_buffer(256) for _ in range(3))
+        name, addr = C.create_string_buffer(256), C.create_string_buffer(256)
         err = C.create_string_buffer(512)
         code = self._lib.ligh_schedule(self._s, model.encode(), resolved.encode(), int(critical),
                                        name, 256, addr, 256, err, 512)
