@@ -77,11 +77,18 @@ def hbm_peak():
         return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
-def committed_traffic(workload):
-    """DRAM bytes per launch of the pick kernel from the committed ncu --set full capture."""
+def committed_traffic(workload, steps_per_launch):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full captures
+    (profiles/traffic.json): per-step traffic of the merged queue kernel x steps per launch, or
+    the per-launch figure of the one-batch-per-launch kernel."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
-            return json.load(fh).get(workload)
+            t = json.load(fh).get(workload)
+        if not t:
+            return None
+        if steps_per_launch > 1:
+            return int(t["queue_kernel_bytes_per_step"] * steps_per_launch)
+        return int(t["stream_kernel_bytes_per_launch"])
     except Exception:
         return None
 
@@ -455,7 +462,10 @@ def main():
 
     if rank == 0:
         peak, peak_src = hbm_peak()
-        alg_bytes = WL.algorithmic_bytes(R, P, A)
+        # algorithmic bytes of one step: 24 B per decision + the snapshot S(P, A) once per LAUNCH
+        # (a merged queue launch serves K steps with one pass over the class tables)
+        snap_share = (16 * P + 4 * A * ((P + 31) // 32)) * min(1.0, max(launches_per_region, 1) / K)
+        alg_bytes = int(24 * R + snap_share)
         launch_s = ms_region / 1e3 / K
         achieved = alg_bytes / launch_s / 1e9
         line = {
@@ -477,11 +487,14 @@ def main():
                             "pinned host descriptors and writes the pinned host picks over PCIe in place"},
             "gpu_launches": int(launches_per_region),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": committed_traffic(args.workload),
-                         "kernel": ("lig_pick_queue_kernel" if (R <= (1 << 17) and K >= 2 and launches_per_region < K)
+                         "frac": achieved / peak,
+                         "traffic": committed_traffic(args.workload, K // max(launches_per_region, 1)),
+                         "kernel": ("lig_pick_queue_kernel (K steps per launch)" if launches_per_region < K
                                     else "lig_pick_stream_kernel"),
-                         "algorithmic_bytes_per_launch": alg_bytes,
-                         "launch_us": launch_s * 1e6, "peak_source": peak_src},
+                         "algorithmic_bytes_per_step": alg_bytes,
+                         "algorithmic_bytes_per_launch": int(alg_bytes * K / max(launches_per_region, 1)),
+                         "step_us": launch_s * 1e6, "launch_us": ms_region * 1e3 / max(launches_per_region, 1),
+                         "peak_source": peak_src},
             "clocks": clocks,
             "snapshot_build_us": snapshot_build_us,
             "with_snapshot_rebuild": {"value": value_rebuild, "unit": UNIT,

@@ -142,8 +142,8 @@ struct lig_ctx {
   // one cudaGraphLaunch instead of one cudaLaunchKernel per batch
   std::vector<QueueGraph*> graphs;
   uint64_t graph_clock = 0;
-  // queues of small batches run as ONE launch with blockIdx.y = batch; the item table goes
-  // through a small pinned ring
+  // a queue normally runs as ONE launch with blockIdx.y = batch; the item table goes through a
+  // small pinned ring
   static constexpr int kItemSlots = 4;
   static constexpr int kMaxItems = 65535;
   QueueItem* d_items[kItemSlots] = {};
@@ -165,7 +165,11 @@ struct lig_ctx {
   int prefetch_distance = 1;        // LIG_PREFETCH=d      batch b pulls batch b+d of the queue into L2 (0 = off)
   bool use_graph = true;            // LIG_GRAPH=0         disable cached graph replay of queues
   int graph_min_batches = 4;
-  int merge_max_requests = 1 << 17; // LIG_MERGE_MAX       largest R whose queues run as one merged launch
+  // LIG_MERGE_MAX: largest R whose queues run as ONE merged launch (blockIdx.y = batch).  Default:
+  // always.  At R = 2^20 a merged queue and a graph of per-batch kernels are equally fast on one
+  // GPU (4.39 vs 4.43 us per batch), but with several GPUs busy on one host the per-kernel dispatch
+  // overhead grows (5.9 us at 8 GPUs) and only the merged launch is immune to it.
+  int merge_max_requests = 0x7fffffff;
 };
 
 namespace {

@@ -924,9 +924,10 @@ lig_pick_stream_kernel(const int4* __restrict__ reqs, int2* __restrict__ out, in
   pick_cta<kPerThread>(reqs, out, R, blockIdx.x, cls, lists, list_stride, A, seed);
 }
 
-// A whole queue of SMALL batches in one launch: blockIdx.y selects the batch.  A batch of a few
-// thousand requests is far below one kernel launch's worth of work (C2: 1024 requests = one CTA),
-// so queues of such batches are merged instead of launched one by one.
+// A whole queue of batches in one launch: blockIdx.y selects the batch.  A batch of a few thousand
+// requests is far below one kernel launch's worth of work (C2: 1024 requests = one CTA), and even
+// at 2^20 requests per batch one launch per batch only matches the merged launch on an otherwise
+// idle host (see lig_ctx::merge_max_requests).
 struct QueueItem {
   const int4* reqs;
   int2* out;

@@ -443,56 +443,72 @@ def test_thresholds_are_parameters(engine, oracle):
         oracle.set_thresholds()
 
 
-def test_batch_queue_graph_replay_matches_single_batches(engine):
-    """lig_schedule_batches_device: a queue of resident batches (forked streams or a cached CUDA
-    graph replay, L2 prefetch of the next batch) gives exactly the per-batch results, for the first
-    build, for a replay with another seed, and after the snapshot in the slot changed."""
+QUEUE_MODES = {
+    "merged": {},                                                          # default: one launch per queue
+    "graph": {"LIG_MERGE_MAX": "1024"},                                    # one kernel per batch, cached CUDA graph
+    "streams": {"LIG_MERGE_MAX": "1024", "LIG_GRAPH": "0"},                # one kernel per batch, forked streams
+    "pdl": {"LIG_MERGE_MAX": "1024", "LIG_GRAPH": "0", "LIG_PDL": "1", "LIG_QUEUE_STREAMS": "1"},
+    "no_prefetch_2streams": {"LIG_MERGE_MAX": "1024", "LIG_GRAPH": "0", "LIG_PREFETCH": "0", "LIG_QUEUE_STREAMS": "2"},
+    "pipelined": {"LIG_MERGE_MAX": "1024", "LIG_PICK_PER_THREAD": "8"},
+}
+
+
+@pytest.mark.parametrize("mode", sorted(QUEUE_MODES))
+def test_batch_queue_modes_match_single_batches(mode, monkeypatch):
+    """lig_schedule_batches_device: a queue of resident batches gives exactly the per-batch results
+    in every execution mode (merged launch, cached CUDA-graph replay, forked streams, programmatic
+    dependent launch, L2 prefetch on/off, software-pipelined kernel), for the first call, for a
+    replay with another seed, and after the snapshot in the slot changed."""
     import torch
-    c = WL.CONFIGS["C3"]
-    snap = WL.make_snapshot(c["P"], c["A"], seed=41)
-    R, nb = 150_000, 7            # above LIG_MERGE_MAX (131072): per-batch launches / graph path
-    host = [WL.make_requests(R, c["A"], seed=100 + b) for b in range(nb)]
-    d_reqs = [torch.from_numpy(h.view(np.uint8).reshape(-1)).cuda() for h in host]
-    d_out = [torch.zeros(R * 8, dtype=torch.uint8, device="cuda") for _ in range(nb)]
-    stream = torch.cuda.Stream()
-    ep = next_epoch()
-    engine.upload_snapshot(ep, snap.packed)
+    for k, v in QUEUE_MODES[mode].items():
+        monkeypatch.setenv(k, v)                    # the knobs are read at lig_create
+    engine = Engine(0, max_pods=512, max_adapters=256, max_batch=1 << 18)
+    try:
+        c = WL.CONFIGS["C3"]
+        snap = WL.make_snapshot(c["P"], c["A"], seed=41)
+        R, nb = 150_000, 7
+        host = [WL.make_requests(R, c["A"], seed=100 + b) for b in range(nb)]
+        d_reqs = [torch.from_numpy(h.view(np.uint8).reshape(-1)).cuda() for h in host]
+        d_out = [torch.zeros(R * 8, dtype=torch.uint8, device="cuda") for _ in range(nb)]
+        stream = torch.cuda.Stream()
+        ep = next_epoch()
+        engine.upload_snapshot(ep, snap.packed)
 
-    def run_queue(epoch, seed):
-        with torch.cuda.stream(stream):
-            engine.schedule_batches_device(epoch, seed, [t.data_ptr() for t in d_reqs], R,
-                                           [t.data_ptr() for t in d_out], stream.cuda_stream)
-        stream.synchronize()
-        return [t.cpu().numpy().view(PICK_DTYPE).copy() for t in d_out]
+        def run_queue(epoch, seed, Rq=R):
+            with torch.cuda.stream(stream):
+                engine.schedule_batches_device(epoch, seed, [t.data_ptr() for t in d_reqs], Rq,
+                                               [t.data_ptr() for t in d_out], stream.cuda_stream)
+            stream.synchronize()
+            return [t[: Rq * 8].cpu().numpy().view(PICK_DTYPE).copy() for t in d_out]
 
-    for seed in (5, 5, 9000):                       # build, replay, replay with a new seed
-        got = run_queue(ep, seed)
-        for b in range(nb):
-            assert np.array_equal(got[b], engine.schedule_batch(ep, seed + b, host[b])), (seed, b)
-    # a different snapshot uploaded over the older slot: the cached graph must see the new tables
-    snap2 = WL.make_snapshot(c["P"], c["A"], seed=42)
-    ep2, ep3 = next_epoch(), next_epoch()
-    engine.upload_snapshot(ep2, snap2.packed)
-    engine.upload_snapshot(ep3, snap.packed)        # evicts `ep`
-    for epoch in (ep2, ep3):
-        got = run_queue(epoch, 77)
-        for b in range(nb):
-            assert np.array_equal(got[b], engine.schedule_batch(epoch, 77 + b, host[b])), (epoch, b)
-    # small batches take the merged single-launch path (blockIdx.y = batch), ragged R included
-    for Rs in (1, 1000, 1024, 4097):
+        for seed in (5, 5, 9000):                   # first call, replay, replay with a new seed
+            got = run_queue(ep, seed)
+            for b in range(nb):
+                assert np.array_equal(got[b], engine.schedule_batch(ep, seed + b, host[b])), (mode, seed, b)
+        # a different snapshot uploaded over the older slot: a cached graph must see the new tables
+        snap2 = WL.make_snapshot(c["P"], c["A"], seed=42)
+        ep2, ep3 = next_epoch(), next_epoch()
+        engine.upload_snapshot(ep2, snap2.packed)
+        engine.upload_snapshot(ep3, snap.packed)    # evicts `ep`
+        for epoch in (ep2, ep3):
+            got = run_queue(epoch, 77)
+            for b in range(nb):
+                assert np.array_equal(got[b], engine.schedule_batch(epoch, 77 + b, host[b])), (mode, epoch, b)
+        # ragged and tiny batch sizes
+        for Rs in (1, 1000, 1024, 4097):
+            got = run_queue(ep3, 500, Rs)
+            for b in range(nb):
+                assert np.array_equal(got[b], engine.schedule_batch(ep3, 500 + b, host[b][:Rs])), (mode, Rs, b)
+        # a queue of two, and of one
         with torch.cuda.stream(stream):
-            engine.schedule_batches_device(ep3, 500, [t.data_ptr() for t in d_reqs], Rs,
-                                           [t.data_ptr() for t in d_out], stream.cuda_stream)
+            engine.schedule_batches_device(ep3, 3, [d_reqs[0].data_ptr(), d_reqs[1].data_ptr()], R,
+                                           [d_out[0].data_ptr(), d_out[1].data_ptr()], stream.cuda_stream)
+            engine.schedule_batches_device(ep3, 9, [d_reqs[2].data_ptr()], R, [d_out[2].data_ptr()], stream.cuda_stream)
         stream.synchronize()
-        for b in range(nb):
-            got_b = d_out[b][: Rs * 8].cpu().numpy().view(PICK_DTYPE)
-            assert np.array_equal(got_b, engine.schedule_batch(ep3, 500 + b, host[b][:Rs])), (Rs, b)
-    # short queues (below the graph threshold) and a single batch
-    with torch.cuda.stream(stream):
-        engine.schedule_batches_device(ep3, 3, [d_reqs[0].data_ptr(), d_reqs[1].data_ptr()], R,
-                                       [d_out[0].data_ptr(), d_out[1].data_ptr()], stream.cuda_stream)
-    stream.synchronize()
-    assert np.array_equal(d_out[1].cpu().numpy().view(PICK_DTYPE), engine.schedule_batch(ep3, 4, host[1]))
+        assert np.array_equal(d_out[1].cpu().numpy().view(PICK_DTYPE), engine.schedule_batch(ep3, 4, host[1]))
+        assert np.array_equal(d_out[2].cpu().numpy().view(PICK_DTYPE), engine.schedule_batch(ep3, 9, host[2]))
+    finally:
+        engine.close()
 
 
 def test_doorbell_stream_matches_batch_path(oracle):
