@@ -130,3 +130,22 @@ def test_product_does_not_touch_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".go", "Makefile")):
                 text = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "oracle" not in text.lower(), f"{f} mentions the oracle"
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/lig.h (the boundary a cgo shim includes) must compile as strict C99 on its own, and
+    the record sizes the kernels assume must hold for the C compiler too."""
+    import subprocess
+    src = tmp_path / "abi.c"
+    src.write_text('#include "lig.h"\n'
+                   '#include "lig_host_c.h"\n'
+                   'typedef char req_is_16[(sizeof(lig_req) == 16) ? 1 : -1];\n'
+                   'typedef char pick_is_8[(sizeof(lig_pick) == 8) ? 1 : -1];\n'
+                   'typedef char thr_is_24[(sizeof(lig_thresholds) == 24) ? 1 : -1];\n'
+                   'int main(void) { return LIG_OK + LIG_ERR_INVALID + (int)LIG_REQ_CRITICAL + LIG_ABI_VERSION; }\n')
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    out = subprocess.run([cc, "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-fsyntax-only",
+                          "-I", os.path.join(ROOT, "include"),
+                          "-I", os.path.join(ROOT, "llm_instance_gateway_b200", "csrc", "host"), str(src)],
+                         capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
