@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define LIG_ABI_VERSION 1
+#define LIG_ABI_VERSION 2
 
 /* ---- per-request status (lig_pick.status) ------------------------------------------------------
  * LIG_OK    Schedule returned a pod, nil                      pkg/ext-proc/scheduling/scheduler.go:120-121
@@ -43,7 +43,9 @@ enum {
   LIG_ERR_CUDA        = -2, /* CUDA runtime/driver failure, or no device                          */
   LIG_ERR_STALE_EPOCH = -3, /* the epoch passed to schedule is not a resident snapshot            */
   LIG_ERR_NO_SNAPSHOT = -4, /* schedule called before any snapshot upload                         */
-  LIG_ERR_RANGE       = -5  /* a host value does not fit the device record (see lig_pack_pods)    */
+  LIG_ERR_RANGE       = -5, /* a host value does not fit the device record (see lig_pack_pods)    */
+  LIG_ERR_BUSY        = -6, /* no free ticket for an asynchronous submit (wait for one first)     */
+  LIG_ERR_NCCL        = -7  /* NCCL missing (dlopen libnccl.so.2 failed) or an NCCL call failed   */
 };
 
 /* ---- request descriptor: 16 bytes, one int4 load on the device --------------------------------
@@ -170,6 +172,18 @@ void  lig_host_free(void* p);
 int lig_schedule_batch(lig_ctx* ctx, uint64_t epoch, uint64_t seed, const lig_req* reqs, int R,
                        lig_pick* out);
 
+/* Asynchronous submit for the one-goroutine-per-stream caller model (handlers/server.go:51, up to
+ * 40 000 concurrent streams, pkg/manifests/ext_proc.yaml:102-105): many threads may have batches
+ * in flight on one ctx at once.  `reqs` and `out` MUST be page-locked (lig_host_alloc /
+ * cudaHostAlloc / cudaHostRegister) and stay untouched until the wait returns.  On success
+ * *ticket identifies the in-flight batch; lig_schedule_wait blocks until its picks are complete and
+ * releases the ticket.  The ctx lock is held only while the work is enqueued, never while waiting.
+ * LIG_ERR_BUSY when all LIG_MAX_TICKETS tickets are in flight. */
+#define LIG_MAX_TICKETS 256
+int lig_schedule_batch_async(lig_ctx* ctx, uint64_t epoch, uint64_t seed, const lig_req* reqs, int R,
+                             lig_pick* out, int* ticket);
+int lig_schedule_wait(lig_ctx* ctx, int ticket);
+
 /* HBM-resident batch: d_reqs / d_out are device pointers (16-byte / 8-byte aligned); the work is
  * enqueued on `stream` and NOT synchronised.  This is the class-table fast path. */
 int lig_schedule_batch_device(lig_ctx* ctx, uint64_t epoch, uint64_t seed, const lig_req* d_reqs,
@@ -213,6 +227,50 @@ int lig_schedule_scan(lig_ctx* ctx, uint64_t epoch, uint64_t seed, const lig_req
  * fast path uses for requests (critical, adapter_id).  `list` must hold P entries. */
 int lig_read_class(lig_ctx* ctx, uint64_t epoch, int critical, int adapter_id, int* status,
                    int* n_survivors, uint16_t* list);
+
+/* ---- several GPUs, one process (the reference runs ONE scheduler per process, main.go:137) ------
+ * A lig_group owns one lig_ctx per listed CUDA device and an NCCL communicator over them
+ * (ncclCommInitAll).  The request batch shards BY REQUEST (decisions are independent given a
+ * frozen snapshot: Schedule never mutates pod metrics, scheduler.go:113-122); the snapshot is
+ * replicated with one ncclBroadcast per refresh tick, received directly into every member's
+ * resident snapshot slot and consumed in place by the class-table build.  Picks need no
+ * collective: device g owns the contiguous shard [R*g/G, R*(g+1)/G) of the result. */
+typedef struct lig_group lig_group;
+int  lig_group_create(lig_group** out, const int* devices, int n_devices, int max_pods,
+                      int max_adapters, int max_batch);
+void lig_group_destroy(lig_group* g);
+int  lig_group_size(const lig_group* g);
+lig_ctx* lig_group_ctx(lig_group* g, int member);   /* member ctx, e.g. for the device-pointer API */
+int  lig_group_set_thresholds(lig_group* g, const lig_thresholds* t);
+/* lig_upload_snapshot for the whole group: one pack, one H2D to member 0, one ncclBroadcast over
+ * NVLink, one class-table build per member.  Resident on every member when it returns. */
+int  lig_group_upload_snapshot(lig_group* g, uint64_t epoch, int P, int A, const double* kv,
+                               const int32_t* q, const uint16_t* n_active,
+                               const uint16_t* max_active, const uint32_t* bitmap_adapter_major);
+/* lig_schedule_batch over the group: contiguous request shards, results in request order.  The
+ * pick of a request depends on (seed, rand_key) only, so the result equals the single-device
+ * result bit for bit.  Page-locked buffers must be portable (lig_host_alloc is). */
+int  lig_group_schedule_batch(lig_group* g, uint64_t epoch, uint64_t seed, const lig_req* reqs,
+                              int R, lig_pick* out);
+
+/* ---- several GPUs, one process per GPU (torchrun-style launch) ----------------------------------
+ * Rank 0 calls lig_comm_unique_id and ships the LIG_COMM_ID_BYTES to the other ranks by any means
+ * (a file, an env var, the launcher's store); every rank then calls lig_comm_init_rank on its own
+ * ctx.  lig_comm_upload_snapshot_device replicates the root's packed blob (device memory on the
+ * root; ignored elsewhere) into every rank's snapshot slot with one ncclBroadcast enqueued on
+ * `stream`, followed by the class-table build on the same stream; nothing is synchronised.
+ * lig_comm_upload_snapshot is the blocking host-array form (arrays read on the root only). */
+#define LIG_COMM_ID_BYTES 128
+int lig_comm_unique_id(void* id /* LIG_COMM_ID_BYTES */);
+int lig_comm_init_rank(lig_ctx* ctx, int n_ranks, int rank, const void* id);
+int lig_comm_upload_snapshot_device(lig_ctx* ctx, uint64_t epoch, int P, int A, const void* d_blob,
+                                    int root, void* stream);
+int lig_comm_upload_snapshot(lig_ctx* ctx, uint64_t epoch, int P, int A, const double* kv,
+                             const int32_t* q, const uint16_t* n_active, const uint16_t* max_active,
+                             const uint32_t* bitmap_adapter_major, int root);
+/* In-place sum of an int32 vector over the ranks (ncclAllReduce on `stream`): the per-pod pick
+ * histogram of the load-feedback mode. */
+int lig_comm_allreduce_i32(lig_ctx* ctx, int32_t* d_values, int n, void* stream);
 
 /* ---- introspection ------------------------------------------------------------------------- */
 const char* lig_last_error(void);            /* thread-local, never NULL */

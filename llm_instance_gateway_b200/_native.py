@@ -13,6 +13,9 @@ LIB_PATH = os.path.join(_HERE, "liblig.so")
 
 LIG_OK, LIG_DROP, LIG_EMPTY = 0, 1, 2
 LIG_ERR_INVALID, LIG_ERR_CUDA, LIG_ERR_STALE_EPOCH, LIG_ERR_NO_SNAPSHOT, LIG_ERR_RANGE = -1, -2, -3, -4, -5
+LIG_ERR_BUSY, LIG_ERR_NCCL = -6, -7
+LIG_MAX_TICKETS, LIG_COMM_ID_BYTES = 256, 128
+LIG_ABI_VERSION = 2
 LIG_REQ_CRITICAL = 1
 LIG_MAX_PODS, LIG_MAX_ADAPTERS = 32768, 65534
 
@@ -24,6 +27,11 @@ EXPORTED_SYMBOLS = (
     "lig_schedule_scan", "lig_read_class", "lig_last_error", "lig_version", "lig_abi_version",
     "lig_device_count", "lig_kernel_launches", "lig_sm_count", "lig_host_alloc", "lig_host_free",
     "lig_stream_capacity", "lig_stream_open", "lig_stream_submit", "lig_stream_close",
+    "lig_schedule_batch_async", "lig_schedule_wait",
+    "lig_group_create", "lig_group_destroy", "lig_group_size", "lig_group_ctx", "lig_group_set_thresholds",
+    "lig_group_upload_snapshot", "lig_group_schedule_batch",
+    "lig_comm_unique_id", "lig_comm_init_rank", "lig_comm_upload_snapshot_device", "lig_comm_upload_snapshot",
+    "lig_comm_allreduce_i32",
 )
 
 
@@ -90,6 +98,22 @@ def load() -> C.CDLL:
     lib.lig_stream_open.argtypes = [vp]
     lib.lig_stream_submit.argtypes = [vp, u64, u64, vp, i32, vp]
     lib.lig_stream_close.argtypes = [vp]
+    lib.lig_schedule_batch_async.argtypes = [vp, u64, u64, vp, i32, vp, C.POINTER(i32)]
+    lib.lig_schedule_wait.argtypes = [vp, i32]
+    lib.lig_group_create.argtypes = [C.POINTER(vp), C.POINTER(i32), i32, i32, i32, i32]
+    lib.lig_group_destroy.argtypes = [vp]
+    lib.lig_group_destroy.restype = None
+    lib.lig_group_size.argtypes = [vp]
+    lib.lig_group_ctx.argtypes = [vp, i32]
+    lib.lig_group_ctx.restype = vp
+    lib.lig_group_set_thresholds.argtypes = [vp, C.POINTER(LigThresholds)]
+    lib.lig_group_upload_snapshot.argtypes = [vp, u64, i32, i32, vp, vp, vp, vp, vp]
+    lib.lig_group_schedule_batch.argtypes = [vp, u64, u64, vp, i32, vp]
+    lib.lig_comm_unique_id.argtypes = [vp]
+    lib.lig_comm_init_rank.argtypes = [vp, i32, i32, vp]
+    lib.lig_comm_upload_snapshot_device.argtypes = [vp, u64, i32, i32, vp, i32, vp]
+    lib.lig_comm_upload_snapshot.argtypes = [vp, u64, i32, i32, vp, vp, vp, vp, vp, i32]
+    lib.lig_comm_allreduce_i32.argtypes = [vp, vp, i32, vp]
     for name in EXPORTED_SYMBOLS:
         getattr(lib, name)  # AttributeError if the library does not export it
     _lib = lib

@@ -1,9 +1,9 @@
 // lig.cu — the C ABI of include/lig.h over the sm_100a kernels of lig_device.cuh.
 //
 // Host-side responsibilities only: context and HBM/pinned allocation, snapshot slots (two resident
-// epochs), stream/event ordering, the chunk-pipelined host-buffer path, error reporting.  There is
-// deliberately no CPU implementation of the scheduling path in this library: if CUDA is missing
-// every entry point fails with LIG_ERR_CUDA.
+// epochs), stream/event ordering, the host-buffer path, error reporting.  There is deliberately no
+// CPU implementation of the scheduling path in this library: if CUDA is missing every entry point
+// fails with LIG_ERR_CUDA.
 #include <cuda_runtime.h>
 
 #include <atomic>
@@ -16,13 +16,15 @@
 #include <vector>
 
 #include "lig_device.cuh"
+#include "lig_internal.hpp"
 
 using namespace lig;
 
 namespace {
-
 thread_local char g_err[512] = "";
+}
 
+namespace ligi {
 int fail(int code, const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -30,16 +32,10 @@ int fail(int code, const char* fmt, ...) {
   va_end(ap);
   return code;
 }
+}  // namespace ligi
+using ligi::fail;
 
-#define CUDA_TRY_RC(expr)                                                                   \
-  do {                                                                                      \
-    cudaError_t e__ = (expr);                                                               \
-    if (e__ != cudaSuccess) {                                                               \
-      *rc = fail(LIG_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__),     \
-                 __FILE__, __LINE__);                                                       \
-      return nullptr;                                                                       \
-    }                                                                                       \
-  } while (0)
+namespace {
 
 #define CUDA_TRY(expr)                                                                      \
   do {                                                                                      \
@@ -86,30 +82,23 @@ struct Slot {
   unsigned char* d_blob = nullptr;
   ClassEntry* d_cls = nullptr;
   uint16_t* d_lists = nullptr;
+  unsigned char* d_ctab = nullptr;  // compact tables (CompactHeader blob): entries + packed lists
+  uint32_t ctab_pool_capacity = 0;  // list entries the compact pool can hold
+  CompactHeader* h_hdr = nullptr;   // pinned copy of the blob's header, valid once `ready` completed
   unsigned char* h_blob = nullptr;  // pinned staging for host uploads
   cudaEvent_t ready = nullptr;      // class tables built
-  cudaEvent_t idle = nullptr;       // last batch that read this slot
+  // Batches that read this slot, possibly on different caller streams: a ring of events, one per
+  // schedule call.  A writer (re-upload, threshold rebuild) waits on every event of the ring; when
+  // the ring wraps, the new reader's stream first waits on the event it is about to re-record, so
+  // the re-recorded event still covers the reader it replaces (transitively).
+  static constexpr int kReaders = 8;
+  cudaEvent_t readers[kReaders] = {};
+  int next_reader = 0;
   uint64_t stamp = 0;               // upload order, to pick the slot to overwrite
 };
 
-constexpr int kPipeStreams = 8;
-constexpr int kHostPipe = 3;
-constexpr int kChunk = 1 << 16;  // requests per chunk of the host-buffer pipeline (1 MiB in)
+constexpr int kLanes = 8;   // streams of the host-buffer path; also the queue streams
 
-}  // namespace
-
-namespace {
-struct QueueGraph {
-  int slot_index = 0, P = 0, A = 0, R = 0, ns = 0, pd = 0, ppt = 0;
-  std::vector<const lig_req*> reqs;
-  std::vector<lig_pick*> outs;
-  cudaGraph_t graph = nullptr;
-  cudaGraphExec_t exec = nullptr;
-  cudaGraphNode_t seed_node = nullptr;
-  uint64_t* d_seed = nullptr;
-  uint64_t last_use = 0;
-};
-constexpr size_t kMaxQueueGraphs = 24;
 }  // namespace
 
 struct lig_ctx {
@@ -118,8 +107,15 @@ struct lig_ctx {
   int sm_count = 0;
   size_t smem_optin = 0;
   lig_thresholds thr{0.8, 5, 50};
-  std::mutex mu;                             // guards everything below
+  // mu guards the slot metadata, the reader rings, lanes/tickets and the item ring.  It is held
+  // only while work is ENQUEUED, never across a host-device synchronisation.  upload_mu serialises
+  // snapshot writers (uploads, threshold rebuilds) and is taken BEFORE mu.  bounce_mu serialises
+  // pageable callers of the host-buffer path (they share the pinned bounce buffers).
+  std::mutex mu;
+  std::mutex upload_mu;
+  std::mutex bounce_mu;
   std::atomic<uint64_t> launches{0};
+  void* comm = nullptr;                      // ncclComm_t, owned by lig_multi.cpp
 
   // ---- snapshots: two resident epochs ----
   Slot slot[2];
@@ -127,7 +123,10 @@ struct lig_ctx {
   cudaStream_t s_up = nullptr;               // snapshot uploads + table builds
 
   // ---- host-buffer batches ----
-  cudaStream_t s_pipe[kPipeStreams] = {};    // also the queue streams of lig_schedule_batches_device
+  cudaStream_t s_lane[kLanes] = {};          // also the queue streams of the per-batch mode
+  int next_lane = 0;
+  cudaEvent_t ticket_ev[LIG_MAX_TICKETS] = {};
+  std::vector<int> free_tickets;
   lig_req* d_reqs = nullptr;                 // device staging (scan test hook)
   lig_pick* d_out = nullptr;
   uint32_t* d_masks = nullptr;               // scan test hook staging (lazily sized)
@@ -137,13 +136,8 @@ struct lig_ctx {
 
   // ---- batch queues (lig_schedule_batches_device) ----
   cudaEvent_t fork = nullptr;
-  cudaEvent_t join[kPipeStreams] = {};
-  // cached CUDA graphs: a queue with the same buffers, shape and snapshot slot is replayed with
-  // one cudaGraphLaunch instead of one cudaLaunchKernel per batch
-  std::vector<QueueGraph*> graphs;
-  uint64_t graph_clock = 0;
-  // a queue normally runs as ONE launch with blockIdx.y = batch; the item table goes through a
-  // small pinned ring
+  cudaEvent_t join[kLanes] = {};
+  // queues longer than kMaxInlineItems carry their item table through a small pinned ring
   static constexpr int kItemSlots = 4;
   static constexpr int kMaxItems = 65535;
   QueueItem* d_items[kItemSlots] = {};
@@ -159,16 +153,21 @@ struct lig_ctx {
   bool stream_open = false;
 
   // ---- tuning knobs, read from the environment at lig_create ----
+  // LIG_PICK_KERNEL = tma (default: persistent CTAs fed by a TMA bulk-copy ring) | loop (persistent
+  // CTAs, LDG with register prefetch) | merged (round 1: one short-lived CTA per 1024 requests)
+  int pick_kernel = 0;              // 0 tma, 1 loop, 2 merged
+  int tma_groups = 2;               // LIG_TMA_GROUPS = 1|2|3 consumer groups of 8 warps per CTA
+  int tma_stages = 4;               // LIG_TMA_STAGES = 2|3|4|6 ring stages of 16 KB per CTA
+  bool tma_bulk_store = false;      // LIG_TMA_BULK_STORE=1: picks leave through TMA bulk stores
+  bool tab_smem = true;             // LIG_TAB_SMEM=0: never pull the compact tables into shared memory
+  int persist_ctas_req = 0;         // LIG_PERSIST_CTAS: resident CTAs per SM (0 = as many as fit)
+  int persist_grid[2][2] = {};      // resident CTAs of the tma variant: [bulk stores?][tables in smem?]
+  int loop_grid[2] = {0, 0};        // resident CTAs of the loop kernel: [tables in smem?]
+  bool host_tma = false;            // LIG_HOST_TMA=1: host-buffer batches through the TMA kernel too
   int pick_per_thread = 4;          // LIG_PICK_PER_THREAD = 1|2|4 (plain) | 8|16 (software-pipelined)
-  int queue_streams = 4;            // LIG_QUEUE_STREAMS   = 1..8 streams a queue is forked over
-  bool use_pdl = false;             // LIG_PDL=1           programmatic dependent launch inside a queue
-  int prefetch_distance = 1;        // LIG_PREFETCH=d      batch b pulls batch b+d of the queue into L2 (0 = off)
-  bool use_graph = true;            // LIG_GRAPH=0         disable cached graph replay of queues
-  int graph_min_batches = 4;
-  // LIG_MERGE_MAX: largest R whose queues run as ONE merged launch (blockIdx.y = batch).  Default:
-  // always.  At R = 2^20 a merged queue and a graph of per-batch kernels are equally fast on one
-  // GPU (4.39 vs 4.43 us per batch), but with several GPUs busy on one host the per-kernel dispatch
-  // overhead grows (5.9 us at 8 GPUs) and only the merged launch is immune to it.
+  int queue_streams = 4;            // LIG_QUEUE_STREAMS   = 1..8 streams of the per-batch mode
+  // LIG_MERGE_MAX (only with LIG_PICK_KERNEL=merged): largest R whose queues run as ONE merged launch
+  // (blockIdx.y = batch); above it, one kernel per batch forked over the queue streams.
   int merge_max_requests = 0x7fffffff;
 };
 
@@ -212,6 +211,21 @@ int resolve_slot(lig_ctx* c, uint64_t epoch, Slot** out) {
   return 0;
 }
 
+// A batch on `st` reads slot s: record it in the slot's reader ring (see Slot::readers).
+int note_reader(Slot& s, cudaStream_t st) {
+  cudaEvent_t ev = s.readers[s.next_reader];
+  s.next_reader = (s.next_reader + 1) % Slot::kReaders;
+  CUDA_TRY(cudaStreamWaitEvent(st, ev, 0));   // no-op unless the ring wrapped onto a live reader
+  CUDA_TRY(cudaEventRecord(ev, st));
+  return 0;
+}
+
+// `writer` must not touch slot s before every recorded reader has finished.
+int wait_readers(Slot& s, cudaStream_t writer) {
+  for (cudaEvent_t ev : s.readers) CUDA_TRY(cudaStreamWaitEvent(writer, ev, 0));
+  return 0;
+}
+
 // Does the tree-walking kernel stage the pod columns in shared memory for this W?
 bool staged_fits(const lig_ctx* c, int W) {
   return scratch_bytes(W) + staged_bytes(W) <= c->smem_optin;
@@ -237,49 +251,146 @@ int launch_class_build(lig_ctx* c, Slot& s, cudaStream_t stream) {
   }
   CUDA_TRY(cudaGetLastError());
   c->launches++;
+  // pack entries + lists into the compact blob and bring its header back for the launch decision
+  lig_class_compact_kernel<<<1, kCompactThreads, 0, stream>>>(s.d_cls, s.d_lists, n_classes, stride, s.d_ctab,
+                                                              s.ctab_pool_capacity);
+  CUDA_TRY(cudaGetLastError());
+  c->launches++;
+  CUDA_TRY(cudaMemcpyAsync(s.h_hdr, s.d_ctab, sizeof(CompactHeader), cudaMemcpyDeviceToHost, stream));
   return 0;
 }
 
-template <int kPerThread>
-cudaError_t launch_pick_variant(int grid, cudaStream_t stream, bool overlap_prev, const int4* in,
-                                int2* out, int R, const uint2* cls, const uint16_t* lists,
-                                int stride, int A, uint64_t seed, const int4* prefetch) {
-  const uint64_t* no_cell = nullptr;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3(kPickThreads);
-  cfg.dynamicSmemBytes = 0;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = overlap_prev ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, lig_pick_stream_kernel<kPerThread>, in, out, R, cls, lists, stride, A,
-                            seed, prefetch, no_cell);
-}
-
-// overlap_prev: the previous operation on `stream` is a pick kernel of the same queue call, whose
-// inputs and outputs this batch does not touch, so this grid may start before that one finished
-// (programmatic dependent launch; completion order on the stream is unchanged).
+// One kernel, one batch, one CTA per 1024 requests (plain LDG/STG): the host-buffer path (the
+// pointers may be page-locked host memory read and written over PCIe in place) and the per-batch
+// queue mode.
 int launch_pick(lig_ctx* c, const Slot& s, uint64_t seed, const lig_req* d_reqs, int R,
-                lig_pick* d_out, cudaStream_t stream, bool overlap_prev = false,
-                const lig_req* prefetch_reqs = nullptr) {
+                lig_pick* d_out, cudaStream_t stream) {
   if (R == 0) return 0;
   const int4* in = reinterpret_cast<const int4*>(d_reqs);
   int2* out = reinterpret_cast<int2*>(d_out);
-  const uint2* cls = reinterpret_cast<const uint2*>(s.d_cls);
-  const int stride = s.P > 0 ? s.P : 1;
+  const uint4* cls = reinterpret_cast<const uint4*>(s.d_cls);
   const int per_cta = kPickThreads * c->pick_per_thread;
   const int grid = (R + per_cta - 1) / per_cta;
-  overlap_prev = overlap_prev && c->use_pdl;
-  const int4* pf = reinterpret_cast<const int4*>(prefetch_reqs);
-  cudaError_t e = cudaSuccess;
   LIG_DISPATCH_PPT(c->pick_per_thread,
-                   e = launch_pick_variant<kPpt>(grid, stream, overlap_prev, in, out, R, cls, s.d_lists,
-                                                 stride, s.A, seed, pf));
-  CUDA_TRY(e);
+                   (lig_pick_stream_kernel<kPpt><<<grid, kPickThreads, 0, stream>>>(in, out, R, cls, s.d_lists, s.A, seed)));
+  CUDA_TRY(cudaGetLastError());
   c->launches++;
+  return 0;
+}
+
+struct PersistVariant {
+  const void* fn = nullptr;
+  int threads = 0;
+  size_t smem = 0;
+};
+
+template <int kGroups, int kStages, bool kBulk, bool kTab>
+PersistVariant make_variant() {
+  PersistVariant v;
+  v.fn = reinterpret_cast<const void*>(&lig_pick_persistent_kernel<kGroups, kStages, kBulk, kTab>);
+  v.threads = persist_threads(kGroups);
+  v.smem = persist_smem_bytes(kGroups, kStages, kBulk, kTab);
+  return v;
+}
+
+template <int kGroups, bool kBulk, bool kTab>
+PersistVariant variant_for_stages(int stages) {
+  switch (stages) {
+    case 2: return make_variant<kGroups, 2, kBulk, kTab>();
+    case 3: return make_variant<kGroups, 3, kBulk, kTab>();
+    case 6: return make_variant<kGroups, 6, kBulk, kTab>();
+    default: return make_variant<kGroups, 4, kBulk, kTab>();
+  }
+}
+
+template <bool kTab>
+PersistVariant variant_for_groups(int groups, int stages, bool bulk) {
+  switch (groups * 2 + (bulk ? 1 : 0)) {
+    case 1 * 2 + 0: return variant_for_stages<1, false, kTab>(stages);
+    case 1 * 2 + 1: return variant_for_stages<1, true, kTab>(stages);
+    case 3 * 2 + 0: return variant_for_stages<3, false, kTab>(stages);
+    case 3 * 2 + 1: return variant_for_stages<3, true, kTab>(stages);
+    case 2 * 2 + 1: return variant_for_stages<2, true, kTab>(stages);
+    default:        return variant_for_stages<2, false, kTab>(stages);
+  }
+}
+
+PersistVariant persist_variant(int groups, int stages, bool bulk, bool tab) {
+  return tab ? variant_for_groups<true>(groups, stages, bulk) : variant_for_groups<false>(groups, stages, bulk);
+}
+
+PersistVariant loop_variant(bool tab) {
+  PersistVariant v;
+  v.fn = tab ? reinterpret_cast<const void*>(&lig_pick_loop_kernel<true>)
+             : reinterpret_cast<const void*>(&lig_pick_loop_kernel<false>);
+  v.threads = kLoopThreads;
+  v.smem = tab ? (size_t)kTabBudget + 16 : 0;
+  return v;
+}
+
+// The persistent TMA-pipelined pick over a queue of n batches of R requests (one launch per
+// <= 2^30 tiles).  Caller holds c->mu.
+int launch_persistent(lig_ctx* c, const Slot& s, uint64_t seed, const lig_req* const* reqs, int R,
+                      lig_pick* const* outs, int n_batches, cudaStream_t st) {
+  if (R == 0 || n_batches == 0) return 0;
+  const uint4* cls = reinterpret_cast<const uint4*>(s.d_cls);
+  const int tile = c->pick_kernel == 1 ? kLoopTile : kTile;
+  const int tpb = (R + tile - 1) / tile;
+  // the compact tables go to shared memory when their header is back (the build has completed)
+  // and they fit the budget; otherwise the strided tables are read through L1 (same results)
+  const bool tab = c->tab_smem && cudaEventQuery(s.ready) == cudaSuccess && s.h_hdr->bytes != 0 &&
+                   s.h_hdr->bytes <= kTabBudget && s.h_hdr->n_classes == 2u * (uint32_t)(s.A + 1);
+  cudaGetLastError();   // cudaEventQuery's cudaErrorNotReady is not an error
+  int per_launch = (1 << 30) / tpb;
+  if (per_launch > lig_ctx::kMaxItems) per_launch = lig_ctx::kMaxItems;
+  if (per_launch < 1) per_launch = 1;
+  for (int lo = 0; lo < n_batches; lo += per_launch) {
+    const int n = (n_batches - lo) < per_launch ? (n_batches - lo) : per_launch;
+    QueueParams qp;
+    qp.n_batches = n;
+    qp.R = R;
+    qp.tiles_per_batch = tpb;
+    qp.total_tiles = n * tpb;
+    qp.dev_items = nullptr;
+    bool aligned = true;   // TMA bulk stores need 16-byte aligned pick buffers (the ABI asks for 8)
+    for (int b = 0; b < n; ++b)
+      if (reinterpret_cast<uintptr_t>(outs[lo + b]) & 15u) aligned = false;
+    int slot = -1;
+    if (n <= kMaxInlineItems) {
+      for (int b = 0; b < n; ++b)
+        qp.items[b] = QueueItem{reinterpret_cast<const int4*>(reqs[lo + b]),
+                                reinterpret_cast<int2*>(outs[lo + b]), seed + (uint64_t)(lo + b)};
+    } else {
+      slot = c->item_slot;
+      c->item_slot = (slot + 1) % lig_ctx::kItemSlots;
+      CUDA_TRY(cudaEventSynchronize(c->items_free[slot]));   // the kernel of 4 long queues ago is done
+      for (int b = 0; b < n; ++b)
+        c->h_items[slot][b] = QueueItem{reinterpret_cast<const int4*>(reqs[lo + b]),
+                                        reinterpret_cast<int2*>(outs[lo + b]), seed + (uint64_t)(lo + b)};
+      CUDA_TRY(cudaMemcpyAsync(c->d_items[slot], c->h_items[slot], sizeof(QueueItem) * (size_t)n,
+                               cudaMemcpyHostToDevice, st));
+      qp.dev_items = c->d_items[slot];
+    }
+    const uint16_t* lists = s.d_lists;
+    int A = s.A;
+    const unsigned char* ctab = s.d_ctab;
+    uint32_t ctab_bytes = tab ? s.h_hdr->bytes : 0u;
+    void* args[6] = {&qp, &cls, &lists, &A, &ctab, &ctab_bytes};
+    if (c->pick_kernel == 1) {
+      const PersistVariant v = loop_variant(tab);
+      const int cap = c->loop_grid[tab ? 1 : 0];
+      const int grid = qp.total_tiles < cap ? qp.total_tiles : cap;
+      CUDA_TRY(cudaLaunchKernel(v.fn, dim3((unsigned)grid), dim3((unsigned)v.threads), args, v.smem, st));
+    } else {
+      const bool bulk = c->tma_bulk_store && aligned;
+      const PersistVariant v = persist_variant(c->tma_groups, c->tma_stages, bulk, tab);
+      const int cap = c->persist_grid[bulk ? 1 : 0][tab ? 1 : 0];
+      const int grid = qp.total_tiles < cap ? qp.total_tiles : cap;
+      CUDA_TRY(cudaLaunchKernel(v.fn, dim3((unsigned)grid), dim3((unsigned)v.threads), args, v.smem, st));
+    }
+    c->launches++;
+    if (slot >= 0) CUDA_TRY(cudaEventRecord(c->items_free[slot], st));   // after the kernel that reads the table
+  }
   return 0;
 }
 
@@ -321,104 +432,6 @@ int check_shape(const lig_ctx* c, int P, int A) {
   if (A < 0 || A > c->max_adapters)
     return fail(LIG_ERR_INVALID, "A=%d outside [0, max_adapters=%d]", A, c->max_adapters);
   return 0;
-}
-
-void destroy_queue_graph(QueueGraph* g) {
-  if (!g) return;
-  if (g->exec) cudaGraphExecDestroy(g->exec);
-  if (g->graph) cudaGraphDestroy(g->graph);
-  if (g->d_seed) cudaFree(g->d_seed);
-  delete g;
-}
-
-template <int kPerThread>
-void* pick_kernel_ptr() { return reinterpret_cast<void*>(&lig_pick_stream_kernel<kPerThread>); }
-
-// Build the graph of one queue: a root node that publishes the seed, then the batches as
-// kernel nodes in `ns` independent chains (batch b after batch b - ns), mirroring the forked
-// streams of the ungraphed path; batch b prefetches batch b + pd.
-int build_queue_graph(const Slot& s, QueueGraph* g, int n_batches) {
-  CUDA_TRY(cudaMalloc(&g->d_seed, sizeof(uint64_t)));
-  CUDA_TRY(cudaGraphCreate(&g->graph, 0));
-  uint64_t seed0 = 0;
-  void* seed_args[2] = {&g->d_seed, &seed0};
-  cudaKernelNodeParams kp = {};
-  kp.func = reinterpret_cast<void*>(&lig_set_seed_kernel);
-  kp.gridDim = dim3(1);
-  kp.blockDim = dim3(1);
-  kp.kernelParams = seed_args;
-  CUDA_TRY(cudaGraphAddKernelNode(&g->seed_node, g->graph, nullptr, 0, &kp));
-  void* fn = nullptr;
-  LIG_DISPATCH_PPT(g->ppt, fn = pick_kernel_ptr<kPpt>());
-  const uint2* cls = reinterpret_cast<const uint2*>(s.d_cls);
-  const uint16_t* lists = s.d_lists;
-  int stride = s.P > 0 ? s.P : 1;
-  int A = s.A, R = g->R;
-  const int per_cta = kPickThreads * g->ppt;
-  std::vector<cudaGraphNode_t> nodes((size_t)n_batches);
-  for (int b = 0; b < n_batches; ++b) {
-    const int4* in = reinterpret_cast<const int4*>(g->reqs[(size_t)b]);
-    int2* out = reinterpret_cast<int2*>(g->outs[(size_t)b]);
-    uint64_t offset = (uint64_t)b;
-    const int4* pf = (g->pd > 0 && b + g->pd < n_batches)
-                         ? reinterpret_cast<const int4*>(g->reqs[(size_t)(b + g->pd)]) : nullptr;
-    const uint64_t* cell = g->d_seed;
-    void* args[11] = {&in, &out, &R, &cls, &lists, &stride, &A, &offset, &pf, &cell, nullptr};
-    cudaKernelNodeParams np = {};
-    np.func = fn;
-    np.gridDim = dim3((unsigned)((R + per_cta - 1) / per_cta));
-    np.blockDim = dim3(kPickThreads);
-    np.kernelParams = args;
-    cudaGraphNode_t dep = b < g->ns ? g->seed_node : nodes[(size_t)(b - g->ns)];
-    CUDA_TRY(cudaGraphAddKernelNode(&nodes[(size_t)b], g->graph, &dep, 1, &np));
-  }
-  CUDA_TRY(cudaGraphInstantiate(&g->exec, g->graph, 0));
-  return 0;
-}
-
-// Find or build the cached graph of this queue; nullptr (and *rc = 0) when graphs do not apply.
-QueueGraph* queue_graph_for(lig_ctx* c, const Slot& s, const lig_req* const* d_reqs, int R,
-                            lig_pick* const* d_out, int n_batches, int ns, int pd, int* rc) {
-  *rc = 0;
-  if (!c->use_graph || n_batches < c->graph_min_batches || R == 0) return nullptr;
-  const int slot_index = (int)(&s - c->slot);
-  for (QueueGraph* g : c->graphs) {
-    if (g->slot_index != slot_index || g->P != s.P || g->A != s.A || g->R != R || g->ns != ns ||
-        g->pd != pd || g->ppt != c->pick_per_thread || (int)g->reqs.size() != n_batches)
-      continue;
-    if (memcmp(g->reqs.data(), d_reqs, (size_t)n_batches * sizeof(void*)) != 0 ||
-        memcmp(g->outs.data(), d_out, (size_t)n_batches * sizeof(void*)) != 0)
-      continue;
-    g->last_use = ++c->graph_clock;
-    return g;
-  }
-  if (c->graphs.size() >= kMaxQueueGraphs && c->stream_open)
-    return nullptr;   // eviction needs a device-wide synchronise, impossible under a resident kernel
-  if (c->graphs.size() >= kMaxQueueGraphs) {   // evict the least recently used
-    size_t victim = 0;
-    for (size_t i = 1; i < c->graphs.size(); ++i)
-      if (c->graphs[i]->last_use < c->graphs[victim]->last_use) victim = i;
-    CUDA_TRY_RC(cudaDeviceSynchronize());
-    destroy_queue_graph(c->graphs[victim]);
-    c->graphs.erase(c->graphs.begin() + (long)victim);
-  }
-  QueueGraph* g = new QueueGraph();
-  g->slot_index = slot_index;
-  g->P = s.P;
-  g->A = s.A;
-  g->R = R;
-  g->ns = ns;
-  g->pd = pd;
-  g->ppt = c->pick_per_thread;
-  g->reqs.assign(d_reqs, d_reqs + n_batches);
-  g->outs.assign(d_out, d_out + n_batches);
-  g->last_use = ++c->graph_clock;
-  if ((*rc = build_queue_graph(s, g, n_batches)) != 0) {
-    destroy_queue_graph(g);
-    return nullptr;
-  }
-  c->graphs.push_back(g);
-  return g;
 }
 
 // Ranges handed out by lig_host_alloc (and the ctx's own staging buffers): known to be pinned and
@@ -466,12 +479,111 @@ T* mapped_device_pointer(T* p) {
   return reinterpret_cast<T*>(at.devicePointer);
 }
 
+// Enqueue one host-buffer batch (device-visible pointers) on a lane and hand back a ticket.
+// Caller holds c->mu.
+int submit_mapped(lig_ctx* c, Slot* s, uint64_t seed, const lig_req* dev_in, int R, lig_pick* dev_out,
+                  int* ticket) {
+  if (c->free_tickets.empty())
+    return fail(LIG_ERR_BUSY, "all %d tickets are in flight: call lig_schedule_wait first", LIG_MAX_TICKETS);
+  const int lane = c->next_lane;
+  c->next_lane = (lane + 1) % kLanes;
+  cudaStream_t st = c->s_lane[lane];
+  CUDA_TRY(cudaStreamWaitEvent(st, s->ready, 0));
+  if (c->host_tma) {
+    if (int rc = launch_persistent(c, *s, seed, &dev_in, R, &dev_out, 1, st)) return rc;
+  } else {
+    if (int rc = launch_pick(c, *s, seed, dev_in, R, dev_out, st)) return rc;
+  }
+  if (int rc = note_reader(*s, st)) return rc;
+  const int t = c->free_tickets.back();
+  CUDA_TRY(cudaEventRecord(c->ticket_ev[t], st));
+  c->free_tickets.pop_back();
+  *ticket = t;
+  return 0;
+}
+
 }  // namespace
+
+// ---- snapshot-writer protocol (lig_internal.hpp) ----------------------------------------------------
+namespace ligi {
+
+int device_of(const lig_ctx* c) { return c->device; }
+int max_batch_of(const lig_ctx* c) { return c->max_batch; }
+void*& comm_of(lig_ctx* c) { return c->comm; }
+static void (*g_comm_destructor)(void*) = nullptr;
+void set_comm_destructor(void (*fn)(void*)) { g_comm_destructor = fn; }
+
+int begin_write(lig_ctx* c, uint64_t epoch, int P, int A, cudaStream_t stream, bool own_stream,
+                SnapshotWrite* w) {
+  if (int rc = check_shape(c, P, A)) return rc;
+  c->upload_mu.lock();
+  cudaError_t e = cudaSetDevice(c->device);
+  if (e != cudaSuccess) {
+    c->upload_mu.unlock();
+    return fail(LIG_ERR_CUDA, "cudaSetDevice(%d) failed: %s", c->device, cudaGetErrorString(e));
+  }
+  cudaStream_t st = own_stream ? c->s_up : stream;
+  int rc = 0;
+  {
+    std::lock_guard<std::mutex> lk(c->mu);
+    Slot& s = victim_slot(c, epoch);
+    s.valid = false;                       // evicted: schedule calls on its old epoch now get STALE_EPOCH
+    rc = wait_readers(s, st);              // batches still reading the old content
+    if (!rc && cudaStreamWaitEvent(st, s.ready, 0) != cudaSuccess)   // an earlier device-side upload of this slot
+      rc = fail(LIG_ERR_CUDA, "cudaStreamWaitEvent failed");
+    s.P = P;
+    s.A = A;
+    s.W = words_for(P);
+    w->slot = &s;
+    w->d_blob = s.d_blob;
+    w->h_blob = s.h_blob;
+  }
+  if (rc) {
+    c->upload_mu.unlock();
+    return rc;
+  }
+  w->bytes = layout_for(P, A).total;
+  w->P = P;
+  w->A = A;
+  w->epoch = epoch;
+  w->stream = st;
+  return 0;
+}
+
+int enqueue_build(lig_ctx* c, SnapshotWrite* w) {
+  Slot& s = *static_cast<Slot*>(w->slot);
+  CUDA_TRY(cudaSetDevice(c->device));
+  if (int rc = launch_class_build(c, s, w->stream)) return rc;
+  CUDA_TRY(cudaEventRecord(s.ready, w->stream));
+  return 0;
+}
+
+int finish_write(lig_ctx* c, SnapshotWrite* w, bool synchronise) {
+  Slot& s = *static_cast<Slot*>(w->slot);
+  int rc = 0;
+  if (synchronise) {
+    cudaSetDevice(c->device);
+    cudaError_t e = cudaStreamSynchronize(w->stream);
+    if (e != cudaSuccess) rc = fail(LIG_ERR_CUDA, "snapshot upload failed: %s", cudaGetErrorString(e));
+  }
+  if (!rc) {
+    std::lock_guard<std::mutex> lk(c->mu);
+    s.epoch = w->epoch;
+    s.stamp = ++c->stamp;
+    s.valid = true;
+  }
+  c->upload_mu.unlock();
+  return rc;
+}
+
+void abort_write(lig_ctx* c, SnapshotWrite*) { c->upload_mu.unlock(); }
+
+}  // namespace ligi
 
 extern "C" {
 
 const char* lig_last_error(void) { return g_err; }
-const char* lig_version(void) { return "lig-b200 0.1 (sm_100a)"; }
+const char* lig_version(void) { return "lig-b200 0.2 (sm_100a)"; }
 int lig_abi_version(void) { return LIG_ABI_VERSION; }
 
 int lig_device_count(void) {
@@ -568,39 +680,93 @@ static int create_impl(lig_ctx* c, int device, int max_pods, int max_adapters, i
   for (auto& s : c->slot) {
     CUDA_TRY(cudaMalloc(&s.d_blob, l.total));
     CUDA_TRY(cudaMalloc(&s.d_cls, n_classes * sizeof(ClassEntry)));
-    CUDA_TRY(cudaMalloc(&s.d_lists, (n_classes + 2) * (size_t)max_pods * sizeof(uint16_t)));
+    CUDA_TRY(cudaMalloc(&s.d_lists, list_pool_entries(n_classes, (size_t)max_pods) * sizeof(uint16_t)));
+    {
+      // the compact pool holds the two default lists plus up to 2 M more entries (4 MB); a
+      // snapshot whose lists do not fit keeps the strided tables only
+      size_t cap = list_pool_entries(n_classes, (size_t)max_pods);
+      const size_t bound = 2 * (size_t)max_pods + 16 + ((size_t)2 << 20);
+      if (cap > bound) cap = bound;
+      s.ctab_pool_capacity = (uint32_t)cap;
+      CUDA_TRY(cudaMalloc(&s.d_ctab, sizeof(CompactHeader) + n_classes * sizeof(ClassEntry) + cap * sizeof(uint16_t) + 16));
+      CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&s.h_hdr), sizeof(CompactHeader), cudaHostAllocDefault));
+      memset(s.h_hdr, 0, sizeof(CompactHeader));
+    }
     CUDA_TRY(cudaHostAlloc(&s.h_blob, l.total, cudaHostAllocDefault));
     CUDA_TRY(cudaEventCreateWithFlags(&s.ready, cudaEventDisableTiming));
-    CUDA_TRY(cudaEventCreateWithFlags(&s.idle, cudaEventDisableTiming));
+    for (auto& ev : s.readers) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   }
   if (const char* e = getenv("LIG_PICK_PER_THREAD")) {
     int v2 = atoi(e);
     if (v2 == 1 || v2 == 2 || v2 == 4 || v2 == 8 || v2 == 16) c->pick_per_thread = v2;
   }
-  if (const char* e = getenv("LIG_PDL")) c->use_pdl = atoi(e) != 0;
-  if (const char* e = getenv("LIG_GRAPH")) c->use_graph = atoi(e) != 0;
+  if (const char* e = getenv("LIG_PICK_KERNEL")) {
+    if (!strcmp(e, "loop")) c->pick_kernel = 1;
+    else if (!strcmp(e, "merged")) c->pick_kernel = 2;
+    else c->pick_kernel = 0;
+  }
+  if (const char* e = getenv("LIG_HOST_TMA")) c->host_tma = atoi(e) != 0;
+  if (const char* e = getenv("LIG_TMA_GROUPS")) {
+    int v2 = atoi(e);
+    if (v2 >= 1 && v2 <= 3) c->tma_groups = v2;
+  }
+  if (const char* e = getenv("LIG_TMA_STAGES")) {
+    int v2 = atoi(e);
+    if (v2 == 2 || v2 == 3 || v2 == 4 || v2 == 6) c->tma_stages = v2;
+  }
+  if (const char* e = getenv("LIG_TMA_BULK_STORE")) c->tma_bulk_store = atoi(e) != 0;
+  if (const char* e = getenv("LIG_TAB_SMEM")) c->tab_smem = atoi(e) != 0;
+  // A consumer group may only wait on a ring stage whose previous phase it consumed itself (an
+  // mbarrier parity wait cannot tell "two phases ahead" from "done"): the stage count must be a
+  // multiple of the group count, so that a group always returns to the same stages.
+  if (c->tma_stages % c->tma_groups != 0) {
+    static const int ok[4][4] = {{0, 0, 0, 0}, {2, 3, 4, 6}, {2, 4, 4, 6}, {3, 3, 6, 6}};
+    const int idx = c->tma_stages == 2 ? 0 : c->tma_stages == 3 ? 1 : c->tma_stages == 4 ? 2 : 3;
+    c->tma_stages = ok[c->tma_groups][idx];
+  }
+  if (const char* e = getenv("LIG_PERSIST_CTAS")) c->persist_ctas_req = atoi(e);
   if (const char* e = getenv("LIG_MERGE_MAX")) c->merge_max_requests = atoi(e);
+  if (const char* e = getenv("LIG_QUEUE_STREAMS")) {
+    int v2 = atoi(e);
+    if (v2 >= 1 && v2 <= kLanes) c->queue_streams = v2;
+  }
+  for (int bulk = 0; bulk < 2; ++bulk)
+    for (int tab = 0; tab < 2; ++tab) {
+      const PersistVariant pv = persist_variant(c->tma_groups, c->tma_stages, bulk != 0, tab != 0);
+      CUDA_TRY(cudaFuncSetAttribute(pv.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pv.smem));
+      int per_sm = 0;
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pv.fn, pv.threads, pv.smem));
+      if (per_sm < 1) return fail(LIG_ERR_CUDA, "the persistent pick kernel does not fit on this device");
+      if (c->persist_ctas_req > 0 && c->persist_ctas_req < per_sm) per_sm = c->persist_ctas_req;
+      c->persist_grid[bulk][tab] = per_sm * c->sm_count;
+    }
+  for (int tab = 0; tab < 2; ++tab) {
+    const PersistVariant pv = loop_variant(tab != 0);
+    CUDA_TRY(cudaFuncSetAttribute(pv.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(pv.smem ? pv.smem : 16)));
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pv.fn, pv.threads, pv.smem));
+    if (per_sm < 1) per_sm = 1;
+    if (c->persist_ctas_req > 0 && c->persist_ctas_req < per_sm) per_sm = c->persist_ctas_req;
+    c->loop_grid[tab] = per_sm * c->sm_count;
+  }
   for (int i = 0; i < lig_ctx::kItemSlots; ++i) {
     CUDA_TRY(cudaMalloc(&c->d_items[i], sizeof(QueueItem) * lig_ctx::kMaxItems));
     CUDA_TRY(cudaHostAlloc(&c->h_items[i], sizeof(QueueItem) * lig_ctx::kMaxItems, cudaHostAllocDefault));
     CUDA_TRY(cudaEventCreateWithFlags(&c->items_free[i], cudaEventDisableTiming));
   }
-  if (const char* e = getenv("LIG_PREFETCH")) {
-    int v2 = atoi(e);
-    if (v2 >= 0 && v2 <= 16) c->prefetch_distance = v2;
-  }
-  if (const char* e = getenv("LIG_QUEUE_STREAMS")) {
-    int v2 = atoi(e);
-    if (v2 >= 1 && v2 <= kPipeStreams) c->queue_streams = v2;
-  }
   CUDA_TRY(cudaEventCreateWithFlags(&c->fork, cudaEventDisableTiming));
   for (auto& ev : c->join) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   CUDA_TRY(cudaStreamCreateWithFlags(&c->s_up, cudaStreamNonBlocking));
-  for (auto& s : c->s_pipe) CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  for (auto& s : c->s_lane) CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  c->free_tickets.reserve(LIG_MAX_TICKETS);
+  for (int i = LIG_MAX_TICKETS - 1; i >= 0; --i) {
+    CUDA_TRY(cudaEventCreateWithFlags(&c->ticket_ev[i], cudaEventDisableTiming));
+    c->free_tickets.push_back(i);
+  }
   CUDA_TRY(cudaMalloc(&c->d_reqs, (size_t)max_batch * sizeof(lig_req)));
   CUDA_TRY(cudaMalloc(&c->d_out, (size_t)max_batch * sizeof(lig_pick)));
-  CUDA_TRY(cudaHostAlloc(&c->h_reqs, (size_t)max_batch * sizeof(lig_req), cudaHostAllocMapped));
-  CUDA_TRY(cudaHostAlloc(&c->h_out, (size_t)max_batch * sizeof(lig_pick), cudaHostAllocMapped));
+  CUDA_TRY(cudaHostAlloc(&c->h_reqs, (size_t)max_batch * sizeof(lig_req), cudaHostAllocMapped | cudaHostAllocPortable));
+  CUDA_TRY(cudaHostAlloc(&c->h_out, (size_t)max_batch * sizeof(lig_pick), cudaHostAllocMapped | cudaHostAllocPortable));
   register_pinned(c->h_reqs, (size_t)max_batch * sizeof(lig_req));
   register_pinned(c->h_out, (size_t)max_batch * sizeof(lig_pick));
   return 0;
@@ -640,13 +806,17 @@ void lig_destroy(lig_ctx* c) {
   cudaSetDevice(c->device);
   lig_stream_close(c);   // a resident doorbell kernel would make the synchronize below wait forever
   cudaDeviceSynchronize();
+  if (c->comm && ligi::g_comm_destructor) ligi::g_comm_destructor(c->comm);
   for (auto& s : c->slot) {
     cudaFree(s.d_blob);
     cudaFree(s.d_cls);
     cudaFree(s.d_lists);
+    cudaFree(s.d_ctab);
+    if (s.h_hdr) cudaFreeHost(s.h_hdr);
     cudaFreeHost(s.h_blob);
     if (s.ready) cudaEventDestroy(s.ready);
-    if (s.idle) cudaEventDestroy(s.idle);
+    for (auto& ev : s.readers)
+      if (ev) cudaEventDestroy(ev);
   }
   if (c->mailbox) cudaFreeHost(c->mailbox);
   if (c->s_doorbell) cudaStreamDestroy(c->s_doorbell);
@@ -655,13 +825,13 @@ void lig_destroy(lig_ctx* c) {
     cudaFreeHost(c->h_items[i]);
     if (c->items_free[i]) cudaEventDestroy(c->items_free[i]);
   }
-  for (QueueGraph* g : c->graphs) destroy_queue_graph(g);
-  c->graphs.clear();
+  for (auto& ev : c->ticket_ev)
+    if (ev) cudaEventDestroy(ev);
   if (c->fork) cudaEventDestroy(c->fork);
   for (auto& ev : c->join)
     if (ev) cudaEventDestroy(ev);
   if (c->s_up) cudaStreamDestroy(c->s_up);
-  for (auto& s : c->s_pipe)
+  for (auto& s : c->s_lane)
     if (s) cudaStreamDestroy(s);
   cudaFree(c->d_reqs);
   cudaFree(c->d_out);
@@ -675,15 +845,19 @@ void lig_destroy(lig_ctx* c) {
 
 int lig_set_thresholds(lig_ctx* c, const lig_thresholds* t) {
   if (!c || !t) return fail(LIG_ERR_INVALID, "lig_set_thresholds: null argument");
-  std::lock_guard<std::mutex> lk(c->mu);
-  c->thr = *t;
-  // resident class tables were built with the old thresholds: rebuild them
+  std::lock_guard<std::mutex> uk(c->upload_mu);
   CUDA_TRY(cudaSetDevice(c->device));
-  for (auto& s : c->slot) {
-    if (!s.valid) continue;
-    CUDA_TRY(cudaStreamWaitEvent(c->s_up, s.idle, 0));
-    if (int rc = launch_class_build(c, s, c->s_up)) return rc;
-    CUDA_TRY(cudaEventRecord(s.ready, c->s_up));
+  {
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->thr = *t;
+    // resident class tables were built with the old thresholds: rebuild them
+    for (auto& s : c->slot) {
+      if (!s.valid) continue;
+      if (int rc = wait_readers(s, c->s_up)) return rc;
+      CUDA_TRY(cudaStreamWaitEvent(c->s_up, s.ready, 0));
+      if (int rc = launch_class_build(c, s, c->s_up)) return rc;
+      CUDA_TRY(cudaEventRecord(s.ready, c->s_up));
+    }
   }
   CUDA_TRY(cudaStreamSynchronize(c->s_up));
   return 0;
@@ -699,49 +873,36 @@ int lig_upload_snapshot(lig_ctx* c, uint64_t epoch, int P, int A, const double* 
                         const int32_t* q, const uint16_t* na, const uint16_t* ma,
                         const uint32_t* bitmap) {
   if (!c) return fail(LIG_ERR_INVALID, "lig_upload_snapshot: ctx is null");
-  if (int rc = check_shape(c, P, A)) return rc;
-  std::lock_guard<std::mutex> lk(c->mu);
-  CUDA_TRY(cudaSetDevice(c->device));
-  Slot& s = victim_slot(c, epoch);
-  // the pinned staging blob of this slot may still be in flight from its previous upload
-  CUDA_TRY(cudaStreamSynchronize(c->s_up));
-  if (int rc = lig_pack_snapshot(s.h_blob, P, A, kv, q, na, ma, bitmap)) return rc;
-  CUDA_TRY(cudaStreamWaitEvent(c->s_up, s.idle, 0));  // batches still reading the old content
-  s.valid = false;
-  CUDA_TRY(cudaMemcpyAsync(s.d_blob, s.h_blob, layout_for(P, A).total, cudaMemcpyHostToDevice,
-                           c->s_up));
-  s.P = P;
-  s.A = A;
-  s.W = words_for(P);
-  if (int rc = launch_class_build(c, s, c->s_up)) return rc;
-  CUDA_TRY(cudaEventRecord(s.ready, c->s_up));
-  CUDA_TRY(cudaStreamSynchronize(c->s_up));
-  s.epoch = epoch;
-  s.stamp = ++c->stamp;
-  s.valid = true;
-  return 0;
+  ligi::SnapshotWrite w;
+  if (int rc = ligi::begin_write(c, epoch, P, A, nullptr, true, &w)) return rc;
+  // The ctx lock is NOT held from here to the publish: batches against the other resident epoch
+  // keep flowing while this one is packed, copied and its tables are built.  The slot's pinned
+  // staging blob is free: the previous upload of this slot synchronised before it returned.
+  int rc = lig_pack_snapshot(w.h_blob, P, A, kv, q, na, ma, bitmap);
+  if (!rc && cudaMemcpyAsync(w.d_blob, w.h_blob, w.bytes, cudaMemcpyHostToDevice, w.stream) != cudaSuccess)
+    rc = fail(LIG_ERR_CUDA, "snapshot H2D copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+  if (!rc) rc = ligi::enqueue_build(c, &w);
+  if (rc) {
+    ligi::abort_write(c, &w);
+    return rc;
+  }
+  return ligi::finish_write(c, &w, true);
 }
 
 int lig_upload_snapshot_device(lig_ctx* c, uint64_t epoch, int P, int A, const void* d_blob,
                                void* stream) {
   if (!c || !d_blob) return fail(LIG_ERR_INVALID, "lig_upload_snapshot_device: null argument");
-  if (int rc = check_shape(c, P, A)) return rc;
-  std::lock_guard<std::mutex> lk(c->mu);
-  CUDA_TRY(cudaSetDevice(c->device));
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  Slot& s = victim_slot(c, epoch);
-  CUDA_TRY(cudaStreamWaitEvent(st, s.idle, 0));
-  CUDA_TRY(cudaStreamWaitEvent(st, s.ready, 0));
-  CUDA_TRY(cudaMemcpyAsync(s.d_blob, d_blob, layout_for(P, A).total, cudaMemcpyDeviceToDevice, st));
-  s.P = P;
-  s.A = A;
-  s.W = words_for(P);
-  if (int rc = launch_class_build(c, s, st)) return rc;
-  CUDA_TRY(cudaEventRecord(s.ready, st));
-  s.epoch = epoch;
-  s.stamp = ++c->stamp;
-  s.valid = true;
-  return 0;
+  ligi::SnapshotWrite w;
+  if (int rc = ligi::begin_write(c, epoch, P, A, static_cast<cudaStream_t>(stream), false, &w)) return rc;
+  int rc = 0;
+  if (cudaMemcpyAsync(w.d_blob, d_blob, w.bytes, cudaMemcpyDeviceToDevice, w.stream) != cudaSuccess)
+    rc = fail(LIG_ERR_CUDA, "snapshot D2D copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+  if (!rc) rc = ligi::enqueue_build(c, &w);
+  if (rc) {
+    ligi::abort_write(c, &w);
+    return rc;
+  }
+  return ligi::finish_write(c, &w, false);
 }
 
 int lig_schedule_batch_device(lig_ctx* c, uint64_t epoch, uint64_t seed, const lig_req* d_reqs,
@@ -751,12 +912,16 @@ int lig_schedule_batch_device(lig_ctx* c, uint64_t epoch, uint64_t seed, const l
   std::lock_guard<std::mutex> lk(c->mu);
   Slot* s = nullptr;
   if (int rc = resolve_slot(c, epoch, &s)) return rc;
+  if (R == 0) return 0;
   CUDA_TRY(cudaSetDevice(c->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CUDA_TRY(cudaStreamWaitEvent(st, s->ready, 0));
-  if (int rc = launch_pick(c, *s, seed, d_reqs, R, d_out, st)) return rc;
-  CUDA_TRY(cudaEventRecord(s->idle, st));
-  return 0;
+  if (c->pick_kernel != 2) {
+    if (int rc = launch_persistent(c, *s, seed, &d_reqs, R, &d_out, 1, st)) return rc;
+  } else {
+    if (int rc = launch_pick(c, *s, seed, d_reqs, R, d_out, st)) return rc;
+  }
+  return note_reader(*s, st);
 }
 
 int lig_schedule_batches_device(lig_ctx* c, uint64_t epoch, uint64_t seed,
@@ -767,81 +932,59 @@ int lig_schedule_batches_device(lig_ctx* c, uint64_t epoch, uint64_t seed,
   std::lock_guard<std::mutex> lk(c->mu);
   Slot* s = nullptr;
   if (int rc = resolve_slot(c, epoch, &s)) return rc;
-  if (n_batches == 0) return 0;
+  if (n_batches == 0 || R == 0) return 0;
+  for (int b = 0; b < n_batches; ++b)
+    if (!d_reqs[b] || !d_out[b])
+      return fail(LIG_ERR_INVALID, "lig_schedule_batches_device: null buffer in batch %d", b);
   CUDA_TRY(cudaSetDevice(c->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CUDA_TRY(cudaStreamWaitEvent(st, s->ready, 0));
-  for (int b = 0; b < n_batches; ++b)
-    if (R > 0 && (!d_reqs[b] || !d_out[b]))
-      return fail(LIG_ERR_INVALID, "lig_schedule_batches_device: null buffer in batch %d", b);
-  // Independent batches may overlap on the device: fork the caller's stream into the ctx's
-  // queue streams round-robin and join back, so the tail of batch b overlaps the head of b+1
-  // while everything stays ordered with respect to `stream`.
-  const int ns = (n_batches > 1) ? c->queue_streams : 1;
-  // L2 prefetch of the next batch only pays while a few batches fit the 126 MB L2 together;
-  // beyond that the prefetched lines are evicted before use and every descriptor is read twice
-  const int pd = ((size_t)R * sizeof(lig_req) <= ((size_t)32 << 20)) ? c->prefetch_distance : 0;
-  if (n_batches >= 2 && R > 0 && R <= c->merge_max_requests) {
-    // small batches: one launch for up to 65535 of them
-    const uint2* cls = reinterpret_cast<const uint2*>(s->d_cls);
-    const int stride = s->P > 0 ? s->P : 1;
+  if (c->pick_kernel != 2) {
+    // default: ONE launch of resident CTAs walks every tile of every batch of the queue
+    if (int rc = launch_persistent(c, *s, seed, d_reqs, R, d_out, n_batches, st)) return rc;
+    return note_reader(*s, st);
+  }
+  const uint4* cls = reinterpret_cast<const uint4*>(s->d_cls);
+  if (n_batches >= 2 && R <= c->merge_max_requests) {
+    // round-1 default: one launch, one short-lived CTA per 1024 requests, blockIdx.y = batch
     const int per_cta = kPickThreads * c->pick_per_thread;
     for (int lo = 0; lo < n_batches; lo += lig_ctx::kMaxItems) {
       const int n = (n_batches - lo) < lig_ctx::kMaxItems ? (n_batches - lo) : lig_ctx::kMaxItems;
       const int slot = c->item_slot;
       c->item_slot = (slot + 1) % lig_ctx::kItemSlots;
-      CUDA_TRY(cudaEventSynchronize(c->items_free[slot]));   // table of 4 queues ago has been copied
+      CUDA_TRY(cudaEventSynchronize(c->items_free[slot]));   // the kernel of 4 queues ago is done
       for (int b = 0; b < n; ++b)
         c->h_items[slot][b] = QueueItem{reinterpret_cast<const int4*>(d_reqs[lo + b]),
                                         reinterpret_cast<int2*>(d_out[lo + b]), seed + (uint64_t)(lo + b)};
       CUDA_TRY(cudaMemcpyAsync(c->d_items[slot], c->h_items[slot], sizeof(QueueItem) * (size_t)n,
                                cudaMemcpyHostToDevice, st));
-      CUDA_TRY(cudaEventRecord(c->items_free[slot], st));
       const dim3 grid((unsigned)((R + per_cta - 1) / per_cta), (unsigned)n);
       LIG_DISPATCH_PPT(c->pick_per_thread,
                        (lig_pick_queue_kernel<kPpt><<<grid, kPickThreads, 0, st>>>(
-                           c->d_items[slot], R, cls, s->d_lists, stride, s->A)));
+                           c->d_items[slot], R, cls, s->d_lists, s->A)));
       CUDA_TRY(cudaGetLastError());
       c->launches++;
+      CUDA_TRY(cudaEventRecord(c->items_free[slot], st));    // after the kernel that reads the table
     }
-    CUDA_TRY(cudaEventRecord(s->idle, st));
-    return 0;
+    return note_reader(*s, st);
   }
-  int grc = 0;
-  if (QueueGraph* g = queue_graph_for(c, *s, d_reqs, R, d_out, n_batches, ns, pd, &grc)) {
-    uint64_t seed_value = seed;
-    void* seed_args[2] = {&g->d_seed, &seed_value};
-    cudaKernelNodeParams kp = {};
-    kp.func = reinterpret_cast<void*>(&lig_set_seed_kernel);
-    kp.gridDim = dim3(1);
-    kp.blockDim = dim3(1);
-    kp.kernelParams = seed_args;
-    CUDA_TRY(cudaGraphExecKernelNodeSetParams(g->exec, g->seed_node, &kp));
-    CUDA_TRY(cudaGraphLaunch(g->exec, st));
-    c->launches += (uint64_t)n_batches + 1;
-    CUDA_TRY(cudaEventRecord(s->idle, st));
-    return 0;
-  }
-  if (grc != 0) return grc;
+  // one kernel per batch, forked round-robin over the ctx's streams and joined back
+  const int ns = (n_batches > 1) ? c->queue_streams : 1;
   if (ns == 1) {
     for (int b = 0; b < n_batches; ++b)
-      if (int rc = launch_pick(c, *s, seed + (uint64_t)b, d_reqs[b], R, d_out[b], st, b > 0,
-                               (pd > 0 && b + pd < n_batches) ? d_reqs[b + pd] : nullptr))
-        return rc;
+      if (int rc = launch_pick(c, *s, seed + (uint64_t)b, d_reqs[b], R, d_out[b], st)) return rc;
   } else {
     CUDA_TRY(cudaEventRecord(c->fork, st));
-    for (int k = 0; k < ns; ++k) CUDA_TRY(cudaStreamWaitEvent(c->s_pipe[k], c->fork, 0));
+    for (int k = 0; k < ns; ++k) CUDA_TRY(cudaStreamWaitEvent(c->s_lane[k], c->fork, 0));
     for (int b = 0; b < n_batches; ++b)
-      if (int rc = launch_pick(c, *s, seed + (uint64_t)b, d_reqs[b], R, d_out[b], c->s_pipe[b % ns],
-                               b >= ns, (pd > 0 && b + pd < n_batches) ? d_reqs[b + pd] : nullptr))
+      if (int rc = launch_pick(c, *s, seed + (uint64_t)b, d_reqs[b], R, d_out[b], c->s_lane[b % ns]))
         return rc;
     for (int k = 0; k < ns; ++k) {
-      CUDA_TRY(cudaEventRecord(c->join[k], c->s_pipe[k]));
+      CUDA_TRY(cudaEventRecord(c->join[k], c->s_lane[k]));
       CUDA_TRY(cudaStreamWaitEvent(st, c->join[k], 0));
     }
   }
-  CUDA_TRY(cudaEventRecord(s->idle, st));
-  return 0;
+  return note_reader(*s, st);
 }
 
 int lig_schedule_scan_device(lig_ctx* c, uint64_t epoch, uint64_t seed, const lig_req* d_reqs,
@@ -851,11 +994,39 @@ int lig_schedule_scan_device(lig_ctx* c, uint64_t epoch, uint64_t seed, const li
   std::lock_guard<std::mutex> lk(c->mu);
   Slot* s = nullptr;
   if (int rc = resolve_slot(c, epoch, &s)) return rc;
+  if (R == 0) return 0;
   CUDA_TRY(cudaSetDevice(c->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CUDA_TRY(cudaStreamWaitEvent(st, s->ready, 0));
   if (int rc = launch_scan(c, *s, seed, d_reqs, R, d_out, d_masks, st)) return rc;
-  CUDA_TRY(cudaEventRecord(s->idle, st));
+  return note_reader(*s, st);
+}
+
+int lig_schedule_batch_async(lig_ctx* c, uint64_t epoch, uint64_t seed, const lig_req* reqs, int R,
+                             lig_pick* out, int* ticket) {
+  if (!c || !ticket || R < 1 || !reqs || !out)
+    return fail(LIG_ERR_INVALID, "lig_schedule_batch_async: bad argument (R must be >= 1)");
+  const lig_req* dev_in = mapped_device_pointer(reqs);
+  lig_pick* dev_out = mapped_device_pointer(out);
+  if (!dev_in || !dev_out)
+    return fail(LIG_ERR_INVALID, "lig_schedule_batch_async needs page-locked buffers (lig_host_alloc)");
+  std::lock_guard<std::mutex> lk(c->mu);
+  Slot* s = nullptr;
+  if (int rc = resolve_slot(c, epoch, &s)) return rc;
+  CUDA_TRY(cudaSetDevice(c->device));
+  return submit_mapped(c, s, seed, dev_in, R, dev_out, ticket);
+}
+
+int lig_schedule_wait(lig_ctx* c, int ticket) {
+  if (!c || ticket < 0 || ticket >= LIG_MAX_TICKETS)
+    return fail(LIG_ERR_INVALID, "lig_schedule_wait: bad ticket %d", ticket);
+  cudaError_t e = cudaEventSynchronize(c->ticket_ev[ticket]);   // no ctx lock while waiting
+  {
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->free_tickets.push_back(ticket);
+  }
+  if (e != cudaSuccess)
+    return fail(LIG_ERR_CUDA, "batch failed on the device: %s", cudaGetErrorString(e));
   return 0;
 }
 
@@ -865,39 +1036,34 @@ int lig_schedule_batch(lig_ctx* c, uint64_t epoch, uint64_t seed, const lig_req*
     return fail(LIG_ERR_INVALID, "lig_schedule_batch: bad argument");
   if (R > c->max_batch)
     return fail(LIG_ERR_INVALID, "R=%d exceeds max_batch=%d", R, c->max_batch);
-  std::lock_guard<std::mutex> lk(c->mu);
-  Slot* s = nullptr;
-  if (int rc = resolve_slot(c, epoch, &s)) return rc;
-  if (R == 0) return 0;
-  CUDA_TRY(cudaSetDevice(c->device));
   // Host buffers are not staged through HBM: the pick kernel reads the descriptors from, and
   // writes the picks to, page-locked host memory directly over PCIe (16 B in / 8 B out per
-  // request, both directions in flight at once, one launch, no copy-engine hop).  Measured on
-  // this pool: 36 GB/s in + 18 GB/s out concurrently vs 22 GB/s for a cudaMemcpyAsync H2D.
-  // Pinned caller buffers (lig_host_alloc, cudaHostAlloc, cudaHostRegister) are used in place;
-  // pageable ones bounce through the ctx's pinned buffers chunk by chunk, the CPU copy of chunk
-  // i+1 overlapping the kernel of chunk i.
-  const lig_req* dev_in = mapped_device_pointer(reqs);
-  lig_pick* dev_out = mapped_device_pointer(out);
-  const int chunk = (dev_in && dev_out) ? R : kChunk;
-  const int n_chunks = (R + chunk - 1) / chunk;
-  const lig_req* stage_in = dev_in ? dev_in : mapped_device_pointer(c->h_reqs);
-  lig_pick* stage_out = dev_out ? dev_out : mapped_device_pointer(c->h_out);
-  if (!stage_in || !stage_out)
-    return fail(LIG_ERR_CUDA, "pinned staging buffers are not device-mapped on this platform");
-  for (int k = 0; k < n_chunks; ++k) {
-    const int lo = k * chunk;
-    const int n = (R - lo) < chunk ? (R - lo) : chunk;
-    cudaStream_t st = c->s_pipe[k % kHostPipe];
-    if (k < kHostPipe) CUDA_TRY(cudaStreamWaitEvent(st, s->ready, 0));
-    if (!dev_in) memcpy(c->h_reqs + lo, reqs + lo, (size_t)n * sizeof(lig_req));
-    if (int rc = launch_pick(c, *s, seed, stage_in + lo, n, stage_out + lo, st)) return rc;
+  // request, both directions in flight at once, one launch, no copy-engine hop).  Pinned caller
+  // buffers (lig_host_alloc, cudaHostAlloc, cudaHostRegister) are used in place; pageable ones
+  // bounce through the ctx's pinned buffers.
+  const lig_req* dev_in = R ? mapped_device_pointer(reqs) : nullptr;
+  lig_pick* dev_out = R ? mapped_device_pointer(out) : nullptr;
+  const bool bounce = R > 0 && !(dev_in && dev_out);
+  std::unique_lock<std::mutex> bk(c->bounce_mu, std::defer_lock);
+  if (bounce) {
+    bk.lock();
+    dev_in = mapped_device_pointer(c->h_reqs);
+    dev_out = mapped_device_pointer(c->h_out);
+    if (!dev_in || !dev_out)
+      return fail(LIG_ERR_CUDA, "pinned staging buffers are not device-mapped on this platform");
+    memcpy(c->h_reqs, reqs, (size_t)R * sizeof(lig_req));
   }
-  for (int k = 0; k < kHostPipe && k < n_chunks; ++k) {
-    CUDA_TRY(cudaEventRecord(s->idle, c->s_pipe[k]));  // last record wins; all are synced below
-    CUDA_TRY(cudaStreamSynchronize(c->s_pipe[k]));
+  int ticket = -1;
+  {
+    std::lock_guard<std::mutex> lk(c->mu);
+    Slot* s = nullptr;
+    if (int rc = resolve_slot(c, epoch, &s)) return rc;
+    if (R == 0) return 0;
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (int rc = submit_mapped(c, s, seed, dev_in, R, dev_out, &ticket)) return rc;
   }
-  if (!dev_out) memcpy(out, c->h_out, (size_t)R * sizeof(lig_pick));
+  if (int rc = lig_schedule_wait(c, ticket)) return rc;
+  if (bounce) memcpy(out, c->h_out, (size_t)R * sizeof(lig_pick));
   return 0;
 }
 
@@ -907,32 +1073,37 @@ int lig_schedule_scan(lig_ctx* c, uint64_t epoch, uint64_t seed, const lig_req* 
     return fail(LIG_ERR_INVALID, "lig_schedule_scan: bad argument");
   if (R > c->max_batch)
     return fail(LIG_ERR_INVALID, "R=%d exceeds max_batch=%d", R, c->max_batch);
-  std::lock_guard<std::mutex> lk(c->mu);
-  Slot* s = nullptr;
-  if (int rc = resolve_slot(c, epoch, &s)) return rc;
-  if (R == 0) return 0;
-  CUDA_TRY(cudaSetDevice(c->device));
-  cudaStream_t st = c->s_pipe[0];
-  const size_t mask_bytes = masks ? (size_t)R * (s->W > 0 ? s->W : 1) * sizeof(uint32_t) : 0;
-  if (mask_bytes > c->d_masks_bytes) {
-    if (c->stream_open)
-      return fail(LIG_ERR_INVALID, "lig_schedule_scan: cannot grow the mask buffer while a stream is open "
-                                   "(cudaFree would wait for the resident doorbell kernel)");
-    CUDA_TRY(cudaStreamSynchronize(st));
-    cudaFree(c->d_masks);
-    c->d_masks = nullptr;
-    c->d_masks_bytes = 0;
-    CUDA_TRY(cudaMalloc(&c->d_masks, mask_bytes));
-    c->d_masks_bytes = mask_bytes;
+  // test hook: serialised by the bounce lock (it uses the ctx's device staging buffers)
+  std::lock_guard<std::mutex> bk(c->bounce_mu);
+  cudaStream_t st = c->s_lane[0];
+  size_t mask_bytes = 0;
+  {
+    std::lock_guard<std::mutex> lk(c->mu);
+    Slot* s = nullptr;
+    if (int rc = resolve_slot(c, epoch, &s)) return rc;
+    if (R == 0) return 0;
+    CUDA_TRY(cudaSetDevice(c->device));
+    mask_bytes = masks ? (size_t)R * (s->W > 0 ? s->W : 1) * sizeof(uint32_t) : 0;
+    if (mask_bytes > c->d_masks_bytes) {
+      if (c->stream_open)
+        return fail(LIG_ERR_INVALID, "lig_schedule_scan: cannot grow the mask buffer while a stream is open "
+                                     "(cudaFree would wait for the resident doorbell kernel)");
+      CUDA_TRY(cudaStreamSynchronize(st));
+      cudaFree(c->d_masks);
+      c->d_masks = nullptr;
+      c->d_masks_bytes = 0;
+      CUDA_TRY(cudaMalloc(&c->d_masks, mask_bytes));
+      c->d_masks_bytes = mask_bytes;
+    }
+    CUDA_TRY(cudaStreamWaitEvent(st, s->ready, 0));
+    CUDA_TRY(cudaMemcpyAsync(c->d_reqs, reqs, (size_t)R * sizeof(lig_req), cudaMemcpyHostToDevice, st));
+    if (int rc = launch_scan(c, *s, seed, c->d_reqs, R, c->d_out, masks ? c->d_masks : nullptr, st))
+      return rc;
+    CUDA_TRY(cudaMemcpyAsync(out, c->d_out, (size_t)R * sizeof(lig_pick), cudaMemcpyDeviceToHost, st));
+    if (masks && s->W > 0)
+      CUDA_TRY(cudaMemcpyAsync(masks, c->d_masks, mask_bytes, cudaMemcpyDeviceToHost, st));
+    if (int rc = note_reader(*s, st)) return rc;
   }
-  CUDA_TRY(cudaStreamWaitEvent(st, s->ready, 0));
-  CUDA_TRY(cudaMemcpyAsync(c->d_reqs, reqs, (size_t)R * sizeof(lig_req), cudaMemcpyHostToDevice, st));
-  if (int rc = launch_scan(c, *s, seed, c->d_reqs, R, c->d_out, masks ? c->d_masks : nullptr, st))
-    return rc;
-  CUDA_TRY(cudaMemcpyAsync(out, c->d_out, (size_t)R * sizeof(lig_pick), cudaMemcpyDeviceToHost, st));
-  if (masks && s->W > 0)
-    CUDA_TRY(cudaMemcpyAsync(masks, c->d_masks, mask_bytes, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaEventRecord(s->idle, st));
   CUDA_TRY(cudaStreamSynchronize(st));
   return 0;
 }
@@ -952,9 +1123,8 @@ int lig_read_class(lig_ctx* c, uint64_t epoch, int critical, int adapter_id, int
   *n_survivors = (int)entry_n(e.info);
   *status = (int)entry_status(e.info);
   if (list && *n_survivors > 0)
-    CUDA_TRY(cudaMemcpy(list, s->d_lists + (size_t)class_list_row(e.info, (uint32_t)cls, 2u * (uint32_t)(s->A + 1)) *
-                                               (size_t)(s->P > 0 ? s->P : 1),
-                        (size_t)*n_survivors * sizeof(uint16_t), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(list, s->d_lists + e.list_off, (size_t)*n_survivors * sizeof(uint16_t),
+                        cudaMemcpyDeviceToHost));
   return 0;
 }
 
@@ -1016,6 +1186,9 @@ int lig_stream_submit(lig_ctx* c, uint64_t epoch, uint64_t seed, const lig_req* 
     return fail(LIG_ERR_INVALID, "lig_stream_submit: bad argument");
   if (n > kMailboxCapacity)
     return fail(LIG_ERR_INVALID, "n=%d exceeds the doorbell capacity %d", n, kMailboxCapacity);
+  // one doorbell round trip at a time: the single mailbox is the resource, and a snapshot upload
+  // must not overwrite the slot while the resident kernel reads it (it is not in any reader ring)
+  std::lock_guard<std::mutex> uk(c->upload_mu);
   std::lock_guard<std::mutex> lk(c->mu);
   if (!c->stream_open) return fail(LIG_ERR_INVALID, "lig_stream_submit: call lig_stream_open first");
   Slot* s = nullptr;
@@ -1029,9 +1202,9 @@ int lig_stream_submit(lig_ctx* c, uint64_t epoch, uint64_t seed, const lig_req* 
   memcpy(mb->reqs, reqs, (size_t)n * sizeof(lig_req));
   mb->count = (uint32_t)n;
   mb->A = (uint32_t)s->A;
-  mb->list_stride = (uint32_t)(s->P > 0 ? s->P : 1);
+  mb->reserved0 = 0;
   mb->seed = seed;
-  mb->cls = reinterpret_cast<const uint2*>(s->d_cls);
+  mb->cls = reinterpret_cast<const uint4*>(s->d_cls);
   mb->lists = s->d_lists;
   const uint32_t ticket = c->next_ticket++;
   reinterpret_cast<std::atomic<uint32_t>*>(&mb->ticket)->store(ticket, std::memory_order_release);

@@ -43,28 +43,33 @@ struct Thr {
   long long q_lora;   // queueingThresholdLoRA   scheduler.go:23
 };
 
-// One entry per request class c = critical * (A + 1) + min(adapter, A); 8 bytes (one uint2 load).
+// One entry per request class c = critical * (A + 1) + min(adapter, A); 16 bytes (one LDG.128).
 // Classes whose survivor set does not depend on the adapter share one of two default lists
-// (rows 2(A+1) and 2(A+1)+1 of the list pool); the others own row c.  Row offsets are in list
-// entries and fit 32 bits: (2 * 65535 + 2) rows x 32768 entries < 2^32.
+// (rows 2(A+1) and 2(A+1)+1 of the list pool); the others own row c.  List offsets are in list
+// entries and fit 32 bits: (2 * 65535 + 3) rows x 32768 entries < 2^32.
 //
-//   info : bits 0-1 status | 2-3 list row selector | 4-8 shift | 9 n is a power of two | 16-31 n
-//          (info & 0xffff0003 is the second word of lig_pick as is: status | n_survivors << 16)
-//   magic: M = ceil(2^(32+shift) / n), shift = ceil(log2 n) - 1, so that for every v < 2^31
-//          floor(v / n) == umulhi(v, M) >> shift   (Granlund-Montgomery, N = 31 bits; n >= 2)
-// With q = floor(v / n), Go's Int31n is k = v - q * n, resampling while v > 2^31-1-(2^31 % n),
-// i.e. while q >= floor(2^31 / n) = floor((2^31-1) / n) + (n is a power of two ? 1 : 0).
+//   info    : bits 0-1 status | 4-8 shift | 16-31 n
+//             (info & 0xffff0003 is the second word of lig_pick as is: status | n_survivors << 16)
+//   magic   : M = ceil(2^(32+shift) / n), shift = ceil(log2 n) - 1, so that for every v < 2^31
+//             floor(v / n) == umulhi(v, M) >> shift   (Granlund-Montgomery, N = 31 bits; n >= 2)
+//   q_limit : floor(2^31 / n).  With q = floor(v / n), Go's Int31n is k = v - q * n, resampling
+//             while v > 2^31-1-(2^31 % n), i.e. while q >= floor(2^31 / n) (never for a power of
+//             two, where v < 2^31 already implies q < 2^31 / n).
+//   list_off: first entry of the class's survivor list in the list pool.  A class without
+//             survivors points at the pool's sentinel entry 0xffff, which sign-extends to
+//             pod_idx = -1: the pick needs no branch on n.
 struct ClassEntry {
   uint32_t info;
   uint32_t magic;
+  uint32_t q_limit;
+  uint32_t list_off;
 };
-enum : uint32_t { kRowOwn = 0, kRowCriticalDefault = 1, kRowSheddableDefault = 2 };
 
 __host__ __device__ inline uint32_t entry_n(uint32_t info) { return info >> 16; }
 __host__ __device__ inline uint32_t entry_status(uint32_t info) { return info & 3u; }
-__host__ __device__ inline uint32_t class_list_row(uint32_t info, uint32_t c, uint32_t n_classes) {
-  const uint32_t sel = (info >> 2) & 3u;
-  return sel == kRowOwn ? c : n_classes + sel - 1u;
+// Entries of the list pool: one row per class, two shared default rows, then the sentinel.
+__host__ __device__ inline size_t list_pool_entries(size_t n_classes, size_t stride) {
+  return (n_classes + 2) * stride + 8;
 }
 
 // Pod metric columns as the tree walk reads them: either the snapshot in global memory (read
@@ -125,16 +130,16 @@ __device__ __forceinline__ uint32_t int31n(uint64_t state, uint32_t n, uint32_t 
   return v % n;
 }
 
-// The same draw with the class entry's precomputed magic (no integer division on the hot path).
-__device__ __forceinline__ uint32_t int31n_magic(uint64_t state, uint32_t info, uint32_t magic) {
-  const uint32_t n = info >> 16;
-  const uint32_t shift = (info >> 4) & 31u;
-  const uint32_t q_limit = (__umulhi(0x7fffffffu, magic) >> shift) + ((info >> 9) & 1u);
+// The same draw with the class entry's precomputed magic and rejection limit (no integer division
+// and no branch on n on the hot path).  n <= 1: magic 0 gives q = 0 < q_limit, k = 0.
+__device__ __forceinline__ uint32_t int31n_entry(uint64_t state, const uint4 e) {
+  const uint32_t n = e.x >> 16;
+  const uint32_t shift = (e.x >> 4) & 31u;
   uint32_t v = splitmix_int31(state);
-  uint32_t q = __umulhi(v, magic) >> shift;
-  while (q >= q_limit) {   // probability < n / 2^31 per draw
+  uint32_t q = __umulhi(v, e.y) >> shift;
+  while (q >= e.z) {   // probability < n / 2^31 per draw
     v = splitmix_int31(state);
-    q = __umulhi(v, magic) >> shift;
+    q = __umulhi(v, e.y) >> shift;
   }
   return n > 1u ? v - q * n : 0u;
 }
@@ -622,20 +627,21 @@ __host__ __device__ inline size_t build_fixed_bytes(int W) {
   return (b + 15) & ~(size_t)15;   // the staged columns behind it are written with 16-byte stores
 }
 
-__device__ __forceinline__ ClassEntry make_entry(uint32_t n, uint32_t status, uint32_t row_sel) {
+__device__ __forceinline__ ClassEntry make_entry(uint32_t n, uint32_t status, uint32_t list_off) {
   ClassEntry e;
-  // n <= 1: magic 0 gives q = 0 for every draw; the power-of-two bit makes the rejection limit 1,
-  // so the first draw is always accepted and k = 0.
-  uint32_t shift = 0, magic = 0, pow2 = 1;
+  // n <= 1: magic 0 gives q = 0 for every draw and the limit 1 accepts the first one: k = 0.
+  uint32_t shift = 0, magic = 0, q_limit = 1;
   if (n >= 2) {
     const uint32_t l = 32u - (uint32_t)__clz(n - 1u);          // ceil(log2 n), 1..15
     shift = l - 1u;
-    pow2 = (n & (n - 1u)) == 0u;
     // ceil(2^(32+shift) / n) < 2^32 because n > 2^(l-1)
     magic = (uint32_t)((((unsigned long long)1 << (32u + shift)) + n - 1u) / n);
+    q_limit = 0x80000000u / n;
   }
-  e.info = status | (row_sel << 2) | (shift << 4) | (pow2 << 9) | (n << 16);
+  e.info = status | (shift << 4) | (n << 16);
   e.magic = magic;
+  e.q_limit = q_limit;
+  e.list_off = list_off;
   return e;
 }
 
@@ -664,10 +670,12 @@ lig_class_build_kernel(SnapView s, Thr thr, ClassEntry* __restrict__ cls,
   const int n_classes = 2 * (A + 1);
   const uint32_t rc_row = (uint32_t)n_classes * (uint32_t)list_stride;        // default list rows
   const uint32_t rs_row = rc_row + (uint32_t)list_stride;
+  const uint32_t none = rs_row + (uint32_t)list_stride;                       // sentinel entry
+  if (blockIdx.x == 0 && threadIdx.x == 0) lists[none] = 0xffffu;             // reads back as pod_idx -1
 
   if (P == 0) {   // critical: predicate node errs on an empty pool -> sheddable branch -> drop
     for (int c = blockIdx.x * kBuildThreads + threadIdx.x; c < n_classes; c += gridDim.x * kBuildThreads)
-      cls[c] = make_entry(0u, (uint32_t)LIG_DROP, kRowOwn);
+      cls[c] = make_entry(0u, (uint32_t)LIG_DROP, none);
     return;
   }
 
@@ -765,7 +773,7 @@ lig_class_build_kernel(SnapView s, Thr thr, ClassEntry* __restrict__ cls,
     const uint32_t* row = a < A ? s.bitmap + (size_t)a * W : nullptr;
     ClassEntry e;
     if (!critical && n_shed == 0) {
-      e = make_entry(0u, (uint32_t)LIG_DROP, kRowOwn);                     // scheduler.go:83-89
+      e = make_entry(0u, (uint32_t)LIG_DROP, none);                        // scheduler.go:83-89
     } else {
       const uint32_t* Bm = critical ? CB : SB;
       const uint32_t* Zm = critical ? (n_low > 0 ? nullptr : CZ) : SZ;
@@ -779,8 +787,8 @@ lig_class_build_kernel(SnapView s, Thr thr, ClassEntry* __restrict__ cls,
         hit = __reduce_add_sync(kFull, hit);
       }
       if (hit == 0) {
-        e = critical ? make_entry(rc_n, rc_status, kRowCriticalDefault)
-                     : make_entry(rs_n, rs_status, kRowSheddableDefault);
+        e = critical ? make_entry(rc_n, rc_status, rc_n ? rc_row : none)
+                     : make_entry(rs_n, rs_status, rs_n ? rs_row : none);
       } else {
         uint32_t n = hit;
         if (Zm) {   // low cost LoRA: (affinity | room) on the least-queuing set     filter.go:163-166
@@ -798,11 +806,109 @@ lig_class_build_kernel(SnapView s, Thr thr, ClassEntry* __restrict__ cls,
         n = sparse_least_kv<kStaged>(f, X, W, lane, n);
         const uint32_t off = (uint32_t)c * (uint32_t)list_stride;
         if (n) compact_mask_to_list(X, W, lane, lists + off);
-        e = make_entry(n, n ? (uint32_t)LIG_OK : (uint32_t)LIG_EMPTY, kRowOwn);
+        e = make_entry(n, n ? (uint32_t)LIG_OK : (uint32_t)LIG_EMPTY, n ? off : none);
       }
     }
-    if (lane == 0) cls[c] = e;
+    if (lane == 0) *reinterpret_cast<uint4*>(cls + c) = make_uint4(e.info, e.magic, e.q_limit, e.list_off);
     __syncwarp();
+  }
+}
+
+// ---- K2a': compact tables ---------------------------------------------------------------------------
+// The survivor lists are tiny in practice (a handful of pods per class after the least-KV stage),
+// but the build above writes them at a stride of P entries so that every warp can work alone.
+// This pass (one CTA, once per snapshot) packs them behind the class entries into ONE contiguous
+// blob that the persistent pick kernels pull into shared memory with a single TMA bulk copy:
+//
+//   [ header 16 B ][ entries: n_classes x 16 B, list_off relative to the pool ][ pool: u16[] ]
+//
+// pool[0] is the 0xffff sentinel (pod_idx -1) every class without survivors points at.  The two
+// default lists are stored once.  If the pool does not fit `pool_capacity` entries the header says
+// so and the pick kernels fall back to the strided tables in global memory.
+struct CompactHeader {
+  uint32_t bytes;         // header + entries + pool, rounded up to 16; 0 = not available
+  uint32_t n_classes;
+  uint32_t pool_entries;
+  uint32_t reserved;
+};
+constexpr int kCompactThreads = 1024;
+
+__global__ void __launch_bounds__(kCompactThreads)
+lig_class_compact_kernel(const ClassEntry* __restrict__ cls, const uint16_t* __restrict__ lists,
+                         int n_classes, int list_stride, unsigned char* __restrict__ blob,
+                         uint32_t pool_capacity) {
+  __shared__ uint32_t warp_sums[kCompactThreads / 32];
+  __shared__ uint32_t carry;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  CompactHeader* hdr = reinterpret_cast<CompactHeader*>(blob);
+  uint4* out = reinterpret_cast<uint4*>(blob + sizeof(CompactHeader));
+  uint16_t* pool = reinterpret_cast<uint16_t*>(blob + sizeof(CompactHeader) + (size_t)n_classes * sizeof(ClassEntry));
+  const uint32_t rc_row = (uint32_t)n_classes * (uint32_t)list_stride;
+  const uint32_t rs_row = rc_row + (uint32_t)list_stride;
+  // the default lists first: their lengths are the n of any class that points at them
+  // (items -2 and -1 of the scan), found by a block-wide search
+  __shared__ uint32_t def_n[2];
+  if (threadIdx.x < 2) def_n[threadIdx.x] = 0;
+  if (threadIdx.x == 0) carry = 1;                       // pool[0] = sentinel
+  __syncthreads();
+  for (int c = threadIdx.x; c < n_classes; c += kCompactThreads) {
+    const ClassEntry e = cls[c];
+    const uint32_t n = entry_n(e.info);
+    if (n && e.list_off == rc_row) def_n[0] = n;         // same value from every writer
+    if (n && e.list_off == rs_row) def_n[1] = n;
+  }
+  __syncthreads();
+  const uint32_t off_rc = 1, off_rs = 1 + def_n[0];
+  if (threadIdx.x == 0) carry = 1 + def_n[0] + def_n[1];
+  __syncthreads();
+  // exclusive scan of the own-row list lengths, kCompactThreads classes per round
+  for (int base = 0; base < n_classes; base += kCompactThreads) {
+    const int c = base + threadIdx.x;
+    ClassEntry e{0, 0, 1, 0};
+    uint32_t n = 0, own = 0;
+    if (c < n_classes) {
+      e = cls[c];
+      n = entry_n(e.info);
+      own = (n && e.list_off == (uint32_t)c * (uint32_t)list_stride) ? n : 0;
+    }
+    uint32_t incl = own;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const uint32_t o = __shfl_up_sync(kFull, incl, off);
+      if (lane >= off) incl += o;
+    }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    uint32_t before = carry;
+    for (int w = 0; w < warp; ++w) before += warp_sums[w];
+    const uint32_t my_off = before + incl - own;
+    __syncthreads();
+    if (threadIdx.x == kCompactThreads - 1) carry = before + incl;
+    if (c < n_classes) {
+      uint32_t off = 0;                                   // no survivors -> the sentinel
+      if (own) {
+        off = my_off;
+        if (my_off + own <= pool_capacity)
+          for (uint32_t k = 0; k < own; ++k) pool[my_off + k] = lists[e.list_off + k];
+      } else if (n) {
+        off = e.list_off == rc_row ? off_rc : off_rs;
+      }
+      out[c] = make_uint4(e.info, e.magic, e.q_limit, off);
+    }
+    __syncthreads();
+  }
+  // the default lists and the sentinel
+  for (uint32_t k = threadIdx.x; k < def_n[0]; k += kCompactThreads) pool[off_rc + k] = lists[rc_row + k];
+  for (uint32_t k = threadIdx.x; k < def_n[1]; k += kCompactThreads) pool[off_rs + k] = lists[rs_row + k];
+  if (threadIdx.x == 0) {
+    pool[0] = 0xffffu;
+    const uint32_t total = carry;
+    const uint32_t bytes = (uint32_t)((sizeof(CompactHeader) + (size_t)n_classes * sizeof(ClassEntry) +
+                                       (size_t)total * sizeof(uint16_t) + 15) & ~(size_t)15);
+    hdr->n_classes = (uint32_t)n_classes;
+    hdr->pool_entries = total;
+    hdr->reserved = 0;
+    hdr->bytes = total <= pool_capacity ? bytes : 0u;
   }
 }
 
@@ -811,29 +917,38 @@ lig_class_build_kernel(SnapView s, Thr thr, ClassEntry* __restrict__ cls,
 // contiguous bytes and every store 256.  All loads of a thread are issued before the first use.
 constexpr int kPickThreads = 256;
 
-__device__ __forceinline__ int2 pick_one(const int4 r, const uint2* __restrict__ cls,
-                                         const uint16_t* __restrict__ lists, uint32_t list_stride,
-                                         uint32_t A, uint64_t seed) {
+__device__ __forceinline__ int2 pick_one(const int4 r, const uint4* __restrict__ cls,
+                                         const uint16_t* __restrict__ lists, uint32_t A,
+                                         uint64_t seed) {
   const uint32_t critical = (uint32_t)r.y & LIG_REQ_CRITICAL;
   const uint64_t key = ((uint64_t)(uint32_t)r.w << 32) | (uint32_t)r.z;
   const uint32_t a = min((uint32_t)r.x, A);          // ids outside [0, A) (negative too) -> A
   const uint32_t c = critical * (A + 1u) + a;
-  const uint2 e = __ldg(cls + c);                    // {info, magic}
-  int pod = -1;
-  if (e.x >> 16) {
-    const uint32_t k = int31n_magic(seed ^ key, e.x, e.y);
-    const uint32_t row = class_list_row(e.x, c, 2u * (A + 1u));
-    pod = (int)__ldg(lists + (row * list_stride + k));
-  }
+  const uint4 e = __ldg(cls + c);                    // {info, magic, q_limit, list_off}
+  const uint32_t k = int31n_entry(seed ^ key, e);
+  // n == 0: list_off is the pool's 0xffff sentinel -> -1
+  const int pod = (int)(short)__ldg(lists + (e.w + k));
   return make_int2(pod, (int)(e.x & 0xffff0003u));   // {pod_idx, status | n_survivors << 16}
+}
+
+// The same pick against the compact tables in shared memory (entries + pool, see CompactHeader).
+__device__ __forceinline__ int2 pick_one_smem(const int4 r, const uint4* tab, const uint16_t* pool,
+                                              uint32_t A, uint64_t seed) {
+  const uint32_t critical = (uint32_t)r.y & LIG_REQ_CRITICAL;
+  const uint64_t key = ((uint64_t)(uint32_t)r.w << 32) | (uint32_t)r.z;
+  const uint32_t a = min((uint32_t)r.x, A);
+  const uint32_t c = critical * (A + 1u) + a;
+  const uint4 e = tab[c];
+  const uint32_t k = int31n_entry(seed ^ key, e);
+  const int pod = (int)(short)pool[e.w + k];
+  return make_int2(pod, (int)(e.x & 0xffff0003u));
 }
 
 // One CTA's share of one batch: kPerThread requests per thread.
 template <int kPerThread>
 __device__ __forceinline__ void pick_cta(const int4* __restrict__ reqs, int2* __restrict__ out, int R,
-                                         int cta, const uint2* __restrict__ cls,
-                                         const uint16_t* __restrict__ lists, int list_stride, int A,
-                                         uint64_t seed) {
+                                         int cta, const uint4* __restrict__ cls,
+                                         const uint16_t* __restrict__ lists, int A, uint64_t seed) {
   constexpr int kPerCta = kPickThreads * kPerThread;
   const int first = cta * kPerCta;
   const int4* src = reqs + first + threadIdx.x;
@@ -858,7 +973,7 @@ __device__ __forceinline__ void pick_cta(const int4* __restrict__ reqs, int2* __
 #pragma unroll
         for (int j = 0; j < kWidth; ++j)
           st_stream_int2(dst + (it * kWidth + j) * kPickThreads,
-                         pick_one(cur[j], cls, lists, (uint32_t)list_stride, (uint32_t)A, seed));
+                         pick_one(cur[j], cls, lists, (uint32_t)A, seed));
 #pragma unroll
         for (int j = 0; j < kWidth; ++j) cur[j] = nxt[j];
       }
@@ -870,7 +985,7 @@ __device__ __forceinline__ void pick_cta(const int4* __restrict__ reqs, int2* __
       if (i < R)
         st_stream_int2(dst + j * kPickThreads,
                        pick_one(ld_stream_int4(src + j * kPickThreads), cls, lists,
-                                (uint32_t)list_stride, (uint32_t)A, seed));
+                                (uint32_t)A, seed));
     }
     return;
   }
@@ -881,7 +996,7 @@ __device__ __forceinline__ void pick_cta(const int4* __restrict__ reqs, int2* __
 #pragma unroll
     for (int j = 0; j < kPerThread; ++j)
       st_stream_int2(dst + j * kPickThreads,
-                     pick_one(r[j], cls, lists, (uint32_t)list_stride, (uint32_t)A, seed));
+                     pick_one(r[j], cls, lists, (uint32_t)A, seed));
   } else {                                 // ragged tail CTA
 #pragma unroll
     for (int j = 0; j < kPerThread; ++j) {
@@ -889,39 +1004,20 @@ __device__ __forceinline__ void pick_cta(const int4* __restrict__ reqs, int2* __
       if (i < R)
         st_stream_int2(dst + j * kPickThreads,
                        pick_one(ld_stream_int4(src + j * kPickThreads), cls, lists,
-                                (uint32_t)list_stride, (uint32_t)A, seed));
+                                (uint32_t)A, seed));
     }
   }
 }
 
-// 8 CTAs/SM (<= 32 registers) so a 2^20-request batch (1024 CTAs) is a single wave on 148 SMs.
+// One batch, one short-lived CTA per kPickThreads * kPerThread requests.  This is the kernel of the
+// host-buffer path: `reqs` / `out` may be page-locked host memory, read and written over PCIe in
+// place.  8 CTAs/SM (<= 32 registers).
 template <int kPerThread>
 __global__ void __launch_bounds__(kPickThreads, kPerThread <= 8 ? 8 : 6)
 lig_pick_stream_kernel(const int4* __restrict__ reqs, int2* __restrict__ out, int R,
-                       const uint2* __restrict__ cls, const uint16_t* __restrict__ lists,
-                       int list_stride, int A, uint64_t seed, const int4* __restrict__ prefetch,
-                       const uint64_t* __restrict__ seed_cell) {
-  constexpr int kPerCta = kPickThreads * kPerThread;
-  // Inside a replayed CUDA graph the per-call seed lives in device memory (written by the
-  // graph's root node); `seed` then only carries the batch's offset within the queue.
-  if (seed_cell != nullptr) seed += __ldg(seed_cell);
-  const int first = blockIdx.x * kPerCta;
-  // Cross-kernel software pipeline: while this batch is being scheduled, pull the CTA's slice of
-  // a LATER batch of the same queue from HBM into the 126 MB L2 with one TMA-family bulk
-  // prefetch (every descriptor still crosses HBM exactly once; it just does so while this
-  // kernel is busy with its class lookups and stores, so HBM never idles at kernel boundaries).
-  if (prefetch != nullptr && threadIdx.x == 0) {
-    const int n = min(kPerCta, R - first);
-    if (n > 0) {
-      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;"
-                   :: "l"(prefetch + first), "r"(n * 16) : "memory");
-    }
-  }
-  // Batches of one queue are independent: let the next batch's grid (launched with programmatic
-  // stream serialization, see launch_pick) start as soon as SM slots free up.  A no-op for a
-  // normally launched successor.
-  asm volatile("griddepcontrol.launch_dependents;");
-  pick_cta<kPerThread>(reqs, out, R, blockIdx.x, cls, lists, list_stride, A, seed);
+                       const uint4* __restrict__ cls, const uint16_t* __restrict__ lists,
+                       int A, uint64_t seed) {
+  pick_cta<kPerThread>(reqs, out, R, blockIdx.x, cls, lists, A, seed);
 }
 
 // A whole queue of batches in one launch: blockIdx.y selects the batch.  A batch of a few thousand
@@ -936,13 +1032,292 @@ struct QueueItem {
 
 template <int kPerThread>
 __global__ void __launch_bounds__(kPickThreads, kPerThread <= 8 ? 8 : 6)
-lig_pick_queue_kernel(const QueueItem* __restrict__ items, int R, const uint2* __restrict__ cls,
-                      const uint16_t* __restrict__ lists, int list_stride, int A) {
+lig_pick_queue_kernel(const QueueItem* __restrict__ items, int R, const uint4* __restrict__ cls,
+                      const uint16_t* __restrict__ lists, int A) {
   const QueueItem* it = items + blockIdx.y;
   const int4* reqs = reinterpret_cast<const int4*>(__ldg(reinterpret_cast<const unsigned long long*>(&it->reqs)));
   int2* out = reinterpret_cast<int2*>(__ldg(reinterpret_cast<const unsigned long long*>(&it->out)));
   const uint64_t seed = __ldg(reinterpret_cast<const unsigned long long*>(&it->seed));
-  pick_cta<kPerThread>(reqs, out, R, blockIdx.x, cls, lists, list_stride, A, seed);
+  pick_cta<kPerThread>(reqs, out, R, blockIdx.x, cls, lists, A, seed);
+}
+
+// ---- K2c: the persistent, TMA-pipelined pick (default for HBM-resident batches) -----------------
+// One launch serves a whole queue of batches with a FIXED grid of resident CTAs.  Every CTA walks
+// the queue's 1024-request tiles (CTA-local tile j = global tile blockIdx.x + j * gridDim.x):
+//   * a producer warp streams each tile's 16 KB of descriptors global -> shared with one TMA bulk
+//     copy (cp.async.bulk, SASS UBLKCP.S.G) into a kStages-deep ring, completion signalled on an
+//     mbarrier (expect_tx), so HBM reads never wait for the compute of an earlier tile;
+//   * kGroups consumer groups of 8 warps take the CTA's tiles in turn (group g: tiles g,
+//     g + kGroups, ...).  A group waits for its tile, takes 4 descriptors per thread out of shared
+//     memory (conflict-free LDS.128) and hands the stage straight back (mbarrier arrive): the ring
+//     only holds bytes in flight, never bytes being worked on, so a few 16 KB stages feed many
+//     warps.  kStages must be a multiple of kGroups: a group then always returns to the stages
+//     whose previous phase it consumed itself, which is what makes the parity wait unambiguous.  Then class lookup + Int31n + list gather from the L1-resident tables;
+//   * picks leave either as plain coalesced 8-byte stores or (kBulkStore) staged in shared memory
+//     and written with one TMA bulk store per tile (UBLKCP.G.S), tracked by bulk async-groups.
+// The CTAs live for the whole queue, so L1 keeps the class tables across tiles and across
+// batches (L1 is invalidated at launch boundaries only) and there is no per-CTA launch/drain.
+constexpr int kTile = 1024;                     // requests per tile: 16 KB in, 8 KB out
+constexpr int kGroupThreads = 256;              // one consumer group: 8 warps x 4 requests per thread
+constexpr int kMaxInlineItems = 96;             // queue items carried in kernel parameters
+
+struct QueueParams {
+  int n_batches;
+  int R;                    // requests per batch
+  int tiles_per_batch;      // ceil(R / kTile)
+  int total_tiles;          // n_batches * tiles_per_batch (< 2^31, the host splits longer queues)
+  const QueueItem* dev_items;             // used when n_batches > kMaxInlineItems
+  QueueItem items[kMaxInlineItems];       // else: the per-batch pointers and seeds, inline
+};
+
+// Shared-memory budget of the compact tables (CompactHeader blob) inside the persistent kernels:
+// 64 KB hold C4's 2050 entries (32 KB) and its 5.5 K list entries (11 KB) with room to spare.
+constexpr uint32_t kTabBudget = 64 * 1024;
+
+__host__ __device__ constexpr int persist_threads(int groups) { return groups * kGroupThreads + 32; }
+__host__ __device__ constexpr size_t persist_smem_bytes(int groups, int stages, bool bulk_store, bool tab_smem) {
+  return (tab_smem ? (size_t)kTabBudget : 0) + (size_t)stages * kTile * 16 +
+         (bulk_store ? (size_t)groups * kTile * 8 : 0) + 2u * (size_t)stages * 8 + 64;
+}
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+               :: "r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = smem_addr(bar);
+  uint32_t done;
+  do {   // try_wait suspends the thread in hardware up to a time limit; loop until the phase flips
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(a), "r"(parity) : "memory");
+  } while (!done);
+}
+// TMA bulk copy global -> shared, completing `bytes` transaction bytes on `bar` (16 B granular).
+__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(smem_addr(dst_smem)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+// TMA bulk copy shared -> global, tracked by the issuing thread's bulk async-group.
+__device__ __forceinline__ void bulk_store(void* dst, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+               :: "l"(dst), "r"(smem_addr(src_smem)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_store_wait_read_all() {
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void group_barrier(int group) {   // named barrier 1 + group: that group's 8 warps
+  asm volatile("bar.sync %0, %1;" :: "r"(group + 1), "n"(kGroupThreads) : "memory");
+}
+
+__device__ __forceinline__ QueueItem queue_item(const QueueParams& qp, int b) {
+  if (qp.n_batches <= kMaxInlineItems) return qp.items[b];
+  QueueItem it;
+  it.reqs = reinterpret_cast<const int4*>(__ldg(reinterpret_cast<const unsigned long long*>(&qp.dev_items[b].reqs)));
+  it.out = reinterpret_cast<int2*>(__ldg(reinterpret_cast<const unsigned long long*>(&qp.dev_items[b].out)));
+  it.seed = __ldg(reinterpret_cast<const unsigned long long*>(&qp.dev_items[b].seed));
+  return it;
+}
+
+// kTabSmem: the compact tables (ctab, ctab_bytes <= kTabBudget) are pulled into shared memory by
+// one TMA bulk copy at CTA start and every lookup is an LDS; otherwise lookups go to the strided
+// tables (cls, lists) through L1.  The host picks the variant (see launch_persistent).
+template <int kGroups, int kStages, bool kBulkStore, bool kTabSmem>
+__global__ void __launch_bounds__(persist_threads(kGroups), (kTabSmem ? 2 : 6) / kGroups > 0 ? (kTabSmem ? 2 : 6) / kGroups : 1)
+lig_pick_persistent_kernel(const __grid_constant__ QueueParams qp, const uint4* __restrict__ cls,
+                           const uint16_t* __restrict__ lists, int A,
+                           const unsigned char* __restrict__ ctab, uint32_t ctab_bytes) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  unsigned char* base = smem + (kTabSmem ? kTabBudget : 0u);
+  int4* in_ring = reinterpret_cast<int4*>(base);                                   // [kStages][kTile]
+  int2* out_stage = reinterpret_cast<int2*>(base + (size_t)kStages * kTile * 16);  // [kGroups][kTile] (kBulkStore)
+  uint64_t* full = reinterpret_cast<uint64_t*>(base + (size_t)kStages * kTile * 16 +
+                                               (kBulkStore ? (size_t)kGroups * kTile * 8 : 0));
+  uint64_t* empty = full + kStages;
+  uint64_t* tab_bar = empty + kStages;
+  const uint4* tab = reinterpret_cast<const uint4*>(smem + sizeof(CompactHeader));
+  const uint16_t* pool = reinterpret_cast<const uint16_t*>(smem + sizeof(CompactHeader) +
+                                                           (size_t)2 * ((size_t)A + 1) * sizeof(ClassEntry));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full + s, 1);                          // the producer's arrive.expect_tx
+      mbar_init(empty + s, kGroupThreads / 32);        // one arrive per warp of the consuming group
+    }
+    mbar_init(tab_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int tpb = qp.tiles_per_batch, total = qp.total_tiles, R = qp.R;
+
+  if (warp == kGroups * (kGroupThreads / 32)) {
+    // ---- producer: one lane feeds the ring, CTA-local tiles in order ----
+    if (lane == 0) {
+      if (kTabSmem) {                                  // the tables first: one bulk copy, L2-resident
+        mbar_arrive_expect_tx(tab_bar, ctab_bytes);
+        bulk_load(smem, ctab, ctab_bytes, tab_bar);
+      }
+      const int step = (int)gridDim.x;
+      int b = (int)blockIdx.x / tpb;
+      int t = (int)blockIdx.x - b * tpb;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int g = (int)blockIdx.x; g < total; g += step) {
+        mbar_wait(empty + stage, phase ^ 1u);          // free (passes at once on the first lap)
+        const QueueItem it = queue_item(qp, b);
+        const uint32_t n = (uint32_t)min(kTile, R - t * kTile);
+        mbar_arrive_expect_tx(full + stage, n * 16u);
+        bulk_load(in_ring + (size_t)stage * kTile, it.reqs + (size_t)t * kTile, n * 16u, full + stage);
+        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        t += step;
+        while (t >= tpb) { t -= tpb; ++b; }
+      }
+    }
+    return;
+  }
+
+  // ---- consumer group `grp`: CTA-local tiles grp, grp + kGroups, ... ----
+  const int grp = warp / (kGroupThreads / 32);
+  const int tid = (int)threadIdx.x - grp * kGroupThreads;
+  const int step = (int)gridDim.x * kGroups;
+  int g = (int)blockIdx.x + grp * (int)gridDim.x;
+  int b = g / tpb;
+  int t = g - b * tpb;
+  int stage = grp % kStages;
+  uint32_t phase = (uint32_t)(grp / kStages) & 1u;
+  if (kTabSmem) mbar_wait(tab_bar, 0);                 // the tables have landed
+  for (; g < total; g += step) {
+    const QueueItem it = queue_item(qp, b);
+    const int n = min(kTile, R - t * kTile);
+    const int4* tile = in_ring + (size_t)stage * kTile + tid;
+    int4 r[4];
+    mbar_wait(full + stage, phase);                    // the tile's bytes have landed
+    if (n == kTile) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) r[j] = tile[j * kGroupThreads];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        r[j] = (tid + j * kGroupThreads < n) ? tile[j * kGroupThreads] : make_int4(0, 0, 0, 0);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty + stage);         // descriptors are in registers: stage is free
+    // this group's next tile is kGroups ring positions further
+    stage += kGroups;
+    while (stage >= kStages) { stage -= kStages; phase ^= 1u; }
+    int2 p[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      p[j] = kTabSmem ? pick_one_smem(r[j], tab, pool, (uint32_t)A, it.seed)
+                      : pick_one(r[j], cls, lists, (uint32_t)A, it.seed);
+    int2* dst = it.out + (size_t)t * kTile + tid;
+    if (kBulkStore && n == kTile) {
+      int2* ob = out_stage + (size_t)grp * kTile;
+      // the group's previous bulk store has finished READING the staging buffer
+      if (tid == 0) bulk_store_wait_read_all();
+      group_barrier(grp);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) ob[tid + j * kGroupThreads] = p[j];
+      fence_proxy_async_smem();                        // generic-proxy writes -> visible to the TMA
+      group_barrier(grp);
+      if (tid == 0) bulk_store(it.out + (size_t)t * kTile, ob, kTile * 8u);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (tid + j * kGroupThreads < n) st_stream_int2(dst + j * kGroupThreads, p[j]);
+    }
+    t += step;
+    while (t >= tpb) { t -= tpb; ++b; }
+  }
+  if (kBulkStore && tid == 0) bulk_store_wait_read_all();   // shared memory must outlive the reads
+}
+
+// ---- K2d: persistent grid-stride pick with register prefetch (no shared memory) ------------------
+// The LDG/STG counterpart of K2c, kept as the A/B reference of the TMA ring: resident CTAs walk
+// a tile sequence of their own (2048-request tiles); the 4 descriptors of a thread's NEXT tile are requested (LDG.128) before
+// the current tile is computed, so every warp always has one tile's worth of loads in flight.
+constexpr int kLoopThreads = 512;   // tile = 2048 requests (4 per thread)
+constexpr int kLoopTile = kLoopThreads * 4;
+
+template <bool kTabSmem>
+__global__ void __launch_bounds__(kLoopThreads, 3)
+lig_pick_loop_kernel(const __grid_constant__ QueueParams qp, const uint4* __restrict__ cls,
+                     const uint16_t* __restrict__ lists, int A,
+                     const unsigned char* __restrict__ ctab, uint32_t ctab_bytes) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  uint64_t* tab_bar = reinterpret_cast<uint64_t*>(smem + kTabBudget);
+  const uint4* tab = reinterpret_cast<const uint4*>(smem + sizeof(CompactHeader));
+  const uint16_t* pool = reinterpret_cast<const uint16_t*>(smem + sizeof(CompactHeader) +
+                                                           (size_t)2 * ((size_t)A + 1) * sizeof(ClassEntry));
+  if (kTabSmem) {
+    if (threadIdx.x == 0) {
+      mbar_init(tab_bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      mbar_arrive_expect_tx(tab_bar, ctab_bytes);
+      bulk_load(smem, ctab, ctab_bytes, tab_bar);
+    }
+  }
+  const int tpb = qp.tiles_per_batch, total = qp.total_tiles, R = qp.R;
+  const int step = (int)gridDim.x;
+  int g = (int)blockIdx.x;
+  int b = g / tpb;
+  int t = g - b * tpb;
+  if (g >= total) return;
+  QueueItem it = queue_item(qp, b);
+  int n = min(kLoopTile, R - t * kLoopTile);
+  int4 cur[4];
+  {
+    const int4* src = it.reqs + (size_t)t * kLoopTile + threadIdx.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      cur[j] = ((int)threadIdx.x + j * kLoopThreads < n) ? ld_stream_int4(src + j * kLoopThreads) : make_int4(0, 0, 0, 0);
+  }
+  if (kTabSmem) mbar_wait(tab_bar, 0);                 // the tables have landed
+  for (;;) {
+    const int g2 = g + step;
+    int b2 = b, t2 = t + step;
+    while (t2 >= tpb) { t2 -= tpb; ++b2; }
+    QueueItem it2 = it;
+    int n2 = 0;
+    int4 nxt[4];
+    if (g2 < total) {
+      it2 = queue_item(qp, b2);
+      n2 = min(kLoopTile, R - t2 * kLoopTile);
+      const int4* src = it2.reqs + (size_t)t2 * kLoopTile + threadIdx.x;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        nxt[j] = ((int)threadIdx.x + j * kLoopThreads < n2) ? ld_stream_int4(src + j * kLoopThreads) : make_int4(0, 0, 0, 0);
+    }
+    int2* dst = it.out + (size_t)t * kLoopTile + threadIdx.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int2 p = kTabSmem ? pick_one_smem(cur[j], tab, pool, (uint32_t)A, it.seed)
+                              : pick_one(cur[j], cls, lists, (uint32_t)A, it.seed);
+      if ((int)threadIdx.x + j * kLoopThreads < n) st_stream_int2(dst + j * kLoopThreads, p);
+    }
+    if (g2 >= total) break;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) cur[j] = nxt[j];
+    g = g2; b = b2; t = t2; it = it2; n = n2;
+  }
 }
 
 // ---- K3: persistent doorbell kernel (streaming micro-batches) ------------------------------------
@@ -959,9 +1334,9 @@ struct alignas(64) Mailbox {
   uint32_t ticket;            // doorbell: last field written (release); kMailboxQuit = leave the kernel
   uint32_t count;
   uint32_t A;
-  uint32_t list_stride;
+  uint32_t reserved0;
   uint64_t seed;
-  const uint2* cls;           // device pointers of the snapshot slot to use
+  const uint4* cls;           // device pointers of the snapshot slot to use
   const uint16_t* lists;
   uint32_t pad0[6];
   // --- written by the device ---
@@ -985,9 +1360,10 @@ __device__ __forceinline__ int4 ld_sys_int4(const void* p) {
                : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
   return r;
 }
-__device__ __forceinline__ uint2 ld_cg_uint2(const uint2* p) {
-  uint2 r;
-  asm volatile("ld.global.cg.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+__device__ __forceinline__ uint4 ld_cg_uint4(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
   return r;
 }
 __device__ __forceinline__ uint32_t ld_cg_u16(const uint16_t* p) {
@@ -996,19 +1372,15 @@ __device__ __forceinline__ uint32_t ld_cg_u16(const uint16_t* p) {
   return r;
 }
 
-__device__ __forceinline__ int2 doorbell_pick(const int4 r, const uint2* cls, const uint16_t* lists,
-                                              uint32_t stride, uint32_t A, uint64_t seed) {
+__device__ __forceinline__ int2 doorbell_pick(const int4 r, const uint4* cls, const uint16_t* lists,
+                                              uint32_t A, uint64_t seed) {
   const uint32_t critical = (uint32_t)r.y & LIG_REQ_CRITICAL;
   const uint64_t key = ((uint64_t)(uint32_t)r.w << 32) | (uint32_t)r.z;
   const uint32_t a = min((uint32_t)r.x, A);
   const uint32_t c = critical * (A + 1u) + a;
-  const uint2 e = ld_cg_uint2(cls + c);
-  int pod = -1;
-  if (e.x >> 16) {
-    const uint32_t k = int31n_magic(seed ^ key, e.x, e.y);
-    const uint32_t row = class_list_row(e.x, c, 2u * (A + 1u));
-    pod = (int)ld_cg_u16(lists + (row * stride + k));
-  }
+  const uint4 e = ld_cg_uint4(cls + c);
+  const uint32_t k = int31n_entry(seed ^ key, e);
+  const int pod = (int)(short)ld_cg_u16(lists + (e.w + k));
   return make_int2(pod, (int)(e.x & 0xffff0003u));
 }
 
@@ -1031,17 +1403,17 @@ lig_doorbell_kernel(Mailbox* mb) {
     // One PCIe round trip for everything a small micro-batch needs: the header (same 64-byte
     // line as the ticket) and this thread's first descriptor are requested together, the
     // descriptor speculatively (the mailbox always holds kMailboxCapacity slots).
-    const int4 h0 = ld_sys_int4(&mb->ticket);          // ticket, count, A, list_stride
+    const int4 h0 = ld_sys_int4(&mb->ticket);          // ticket, count, A, -
     const int4 h1 = ld_sys_int4(&mb->seed);            // seed lo/hi, cls lo/hi
     const int4 h2 = ld_sys_int4(&mb->lists);           // lists lo/hi, pad
     int4 r = ld_sys_int4(&mb->reqs[threadIdx.x]);
-    const uint32_t count = (uint32_t)h0.y, A = (uint32_t)h0.z, stride = (uint32_t)h0.w;
+    const uint32_t count = (uint32_t)h0.y, A = (uint32_t)h0.z;
     const uint64_t seed = ((uint64_t)(uint32_t)h1.y << 32) | (uint32_t)h1.x;
-    const uint2* cls = reinterpret_cast<const uint2*>(((uint64_t)(uint32_t)h1.w << 32) | (uint32_t)h1.z);
+    const uint4* cls = reinterpret_cast<const uint4*>(((uint64_t)(uint32_t)h1.w << 32) | (uint32_t)h1.z);
     const uint16_t* lists = reinterpret_cast<const uint16_t*>(((uint64_t)(uint32_t)h2.y << 32) | (uint32_t)h2.x);
     for (uint32_t i = threadIdx.x; i < count; i += kPickThreads) {
       if (i != threadIdx.x) r = ld_sys_int4(&mb->reqs[i]);
-      const int2 p = doorbell_pick(r, cls, lists, stride, A, seed);
+      const int2 p = doorbell_pick(r, cls, lists, A, seed);
       asm volatile("st.relaxed.sys.global.v2.s32 [%0], {%1, %2};"
                    :: "l"(reinterpret_cast<int2*>(&mb->picks[i])), "r"(p.x), "r"(p.y) : "memory");
     }
@@ -1051,9 +1423,6 @@ lig_doorbell_kernel(Mailbox* mb) {
     ++ticket;
   }
 }
-
-// Root node of a cached queue graph: publishes the call's seed to the graph's kernels.
-__global__ void lig_set_seed_kernel(uint64_t* cell, uint64_t value) { *cell = value; }
 
 // ---- K1: direct scan -------------------------------------------------------------------------------
 template <bool kStaged>

@@ -12,16 +12,21 @@ from .packer import PICK_DTYPE, REQ_DTYPE, PackedSnapshot, _ptr
 
 class Engine:
     def __init__(self, device: int = 0, max_pods: int = 4096, max_adapters: int = 1024,
-                 max_batch: int = 1 << 20):
+                 max_batch: int = 1 << 20, _borrowed_ctx=None):
         self._lib = N.load()
-        self._ctx = C.c_void_p()
-        N.check(self._lib.lig_create(C.byref(self._ctx), device, max_pods, max_adapters, max_batch))
+        self._owned = _borrowed_ctx is None
+        if self._owned:
+            self._ctx = C.c_void_p()
+            N.check(self._lib.lig_create(C.byref(self._ctx), device, max_pods, max_adapters, max_batch))
+        else:
+            self._ctx = C.c_void_p(_borrowed_ctx)      # a member of an EngineGroup
         self.device = device
         self.max_batch = max_batch
 
     def close(self) -> None:
         if getattr(self, "_ctx", None):
-            self._lib.lig_destroy(self._ctx)
+            if self._owned:
+                self._lib.lig_destroy(self._ctx)
             self._ctx = None
 
     def __del__(self):
@@ -63,6 +68,41 @@ class Engine:
 
     def schedule_batch_ptr(self, epoch: int, seed: int, h_reqs: int, R: int, h_out: int) -> None:
         N.check(self._lib.lig_schedule_batch(self._ctx, epoch, seed, h_reqs, R, h_out))
+
+    def schedule_batch_async(self, epoch: int, seed: int, h_reqs: int, R: int, h_out: int) -> int:
+        """Page-locked buffers only; returns a ticket for schedule_wait."""
+        t = C.c_int(-1)
+        N.check(self._lib.lig_schedule_batch_async(self._ctx, epoch, seed, h_reqs, R, h_out, C.byref(t)))
+        return t.value
+
+    def schedule_wait(self, ticket: int) -> None:
+        N.check(self._lib.lig_schedule_wait(self._ctx, ticket))
+
+    # ---- one process per GPU: NCCL inside the library ----
+    def comm_unique_id(self) -> bytes:
+        buf = (C.c_char * N.LIG_COMM_ID_BYTES)()
+        N.check(self._lib.lig_comm_unique_id(buf))
+        return bytes(buf)
+
+    def comm_init_rank(self, n_ranks: int, rank: int, unique_id: bytes) -> None:
+        buf = (C.c_char * N.LIG_COMM_ID_BYTES).from_buffer_copy(unique_id)
+        N.check(self._lib.lig_comm_init_rank(self._ctx, n_ranks, rank, buf))
+
+    def comm_upload_snapshot_device(self, epoch: int, P: int, A: int, d_blob: int, root: int = 0,
+                                    stream: int = 0) -> None:
+        N.check(self._lib.lig_comm_upload_snapshot_device(self._ctx, epoch, P, A, d_blob or None, root,
+                                                          stream or None))
+
+    def comm_upload_snapshot(self, epoch: int, P: int, A: int, snap: Optional[PackedSnapshot], root: int = 0) -> None:
+        if snap is None:
+            N.check(self._lib.lig_comm_upload_snapshot(self._ctx, epoch, P, A, None, None, None, None, None, root))
+        else:
+            N.check(self._lib.lig_comm_upload_snapshot(self._ctx, epoch, P, A, _ptr(snap.kv), _ptr(snap.q),
+                                                       _ptr(snap.n_active), _ptr(snap.max_active),
+                                                       _ptr(snap.bitmap), root))
+
+    def comm_allreduce_i32(self, d_values: int, n: int, stream: int = 0) -> None:
+        N.check(self._lib.lig_comm_allreduce_i32(self._ctx, d_values, n, stream or None))
 
     def schedule_scan(self, epoch: int, seed: int, reqs: np.ndarray, want_masks: bool = True,
                       W: int = 0) -> Tuple[np.ndarray, Optional[np.ndarray]]:
@@ -122,3 +162,62 @@ class Engine:
     @property
     def sm_count(self) -> int:
         return int(self._lib.lig_sm_count(self._ctx))
+
+
+class EngineGroup:
+    """Several GPUs owned by one process (lig_group_*): the snapshot is replicated with one in-library
+    ncclBroadcast per upload, the request batch shards contiguously, results stay in request order."""
+
+    def __init__(self, devices, max_pods: int = 4096, max_adapters: int = 1024, max_batch: int = 1 << 20):
+        self._lib = N.load()
+        self._g = C.c_void_p()
+        arr = (C.c_int * len(devices))(*devices)
+        N.check(self._lib.lig_group_create(C.byref(self._g), arr, len(devices), max_pods, max_adapters, max_batch))
+        self.devices = list(devices)
+        self.max_batch = max_batch
+
+    def close(self) -> None:
+        if getattr(self, "_g", None):
+            self._lib.lig_group_destroy(self._g)
+            self._g = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def size(self) -> int:
+        return int(self._lib.lig_group_size(self._g))
+
+    def member(self, i: int) -> Engine:
+        ctx = self._lib.lig_group_ctx(self._g, i)
+        if not ctx:
+            raise IndexError(i)
+        return Engine(self.devices[i], max_batch=self.max_batch, _borrowed_ctx=ctx)
+
+    def set_thresholds(self, kv_cache_threshold=0.8, queue_threshold_critical=5, queueing_threshold_lora=50) -> None:
+        t = N.LigThresholds(kv_cache_threshold, queue_threshold_critical, queueing_threshold_lora)
+        N.check(self._lib.lig_group_set_thresholds(self._g, C.byref(t)))
+
+    def upload_snapshot(self, epoch: int, snap: PackedSnapshot) -> None:
+        N.check(self._lib.lig_group_upload_snapshot(self._g, epoch, snap.P, snap.A, _ptr(snap.kv), _ptr(snap.q),
+                                                    _ptr(snap.n_active), _ptr(snap.max_active), _ptr(snap.bitmap)))
+
+    def schedule_batch(self, epoch: int, seed: int, reqs: np.ndarray, out: Optional[np.ndarray] = None) -> np.ndarray:
+        assert reqs.dtype == REQ_DTYPE and reqs.flags.c_contiguous
+        R = int(reqs.shape[0])
+        if out is None:
+            out = np.empty(R, dtype=PICK_DTYPE)
+        N.check(self._lib.lig_group_schedule_batch(self._g, epoch, seed, _ptr(reqs), R, _ptr(out)))
+        return out
+
+    def schedule_batch_ptr(self, epoch: int, seed: int, h_reqs: int, R: int, h_out: int) -> None:
+        N.check(self._lib.lig_group_schedule_batch(self._g, epoch, seed, h_reqs, R, h_out))

@@ -96,6 +96,42 @@ int lig_oracle_soa_schedule_batch(int P, int A, const double* kv, const int32_t*
                                   const lig_oracle_req* reqs, int R, uint64_t seed,
                                   lig_oracle_pick* out, uint32_t* masks, int nthreads);
 
+/* "Class-table CPU" fairness datapoint and fast whole-shard checker (lig_oracle_classtab.c): the
+ * same algorithmic restructuring the GPU path uses, on the host — the tree is walked once per
+ * request class (critical, adapter) per snapshot (2(A+1) walks, `nthreads` threads), a request is
+ * then a table lookup + Int31n + one list read. */
+typedef struct lig_oracle_classtab lig_oracle_classtab;
+lig_oracle_classtab* lig_oracle_classtab_build(int P, int A, const double* kv, const int32_t* q,
+                                               const uint16_t* n_active, const uint16_t* max_active,
+                                               const uint32_t* bitmap_adapter_major,
+                                               double kv_cache_threshold, int64_t queue_threshold_critical,
+                                               int64_t queueing_threshold_lora, int nthreads);
+void lig_oracle_classtab_free(lig_oracle_classtab*);
+int lig_oracle_classtab_schedule_batch(const lig_oracle_classtab*, const lig_oracle_req* reqs, int R,
+                                       uint64_t seed, lig_oracle_pick* out, int nthreads);
+int lig_oracle_classtab_class(const lig_oracle_classtab*, int critical, int adapter_id, int* status,
+                              int* n, uint16_t* list);
+
+/* ---- the step before Schedule (lig_oracle_models.c): handlers/request.go:42-56,
+ * backend/datastore.go:70-105.  A lig_oracle_models is the datastore's InferenceModels map keyed by
+ * a dense model id.  Draw parity against Go's seeded source is UNPINNED (see the file header); the
+ * draw is defined on the request's private SplitMix64 stream seed ^ rand_key ^ LIGO_DRAW_DOMAIN. */
+#define LIGO_DRAW_DOMAIN 0xA0761D6478BD642Full
+enum { LIGO_NO_MODEL = 3, LIGO_NO_TARGET = 4 };
+typedef struct { int16_t pod_idx; uint8_t status; uint8_t target_idx; } lig_oracle_mpick;   /* 4 B */
+typedef struct lig_oracle_models lig_oracle_models;
+lig_oracle_models* lig_oracle_models_new(int n_models);
+void lig_oracle_models_free(lig_oracle_models*);
+int lig_oracle_models_set(lig_oracle_models*, int i, const char* name, int critical,
+                          const char* const* target_names, const int32_t* weights, int n_targets);
+int lig_oracle_weighted_select(const lig_oracle_models*, int model, int32_t randomVal);
+int lig_oracle_random_weighted_draw(const lig_oracle_models*, int model, uint64_t state);
+int lig_oracle_resolve(const lig_oracle_models*, int model, uint64_t seed, uint64_t rand_key,
+                       const char** resolved, int* critical, int* target_idx);
+int lig_oracle_schedule_models_batch(const lig_oracle_pool*, const lig_oracle_models*,
+                                     const uint32_t* model_ids, int R, uint64_t seed,
+                                     uint64_t first_index, lig_oracle_mpick* out);
+
 /* The pick primitives, exposed for known-answer tests. */
 uint64_t lig_oracle_splitmix64_next(uint64_t* state);
 int32_t  lig_oracle_int31n(uint64_t* state, int32_t n);

@@ -19,24 +19,8 @@
 #include <string.h>
 
 #include "lig_oracle.h"
+#include "lig_oracle_soa_internal.h"
 
-typedef struct {
-  int P, A, W64;            /* W64 = ceil(P / 64) */
-  const double* kv;
-  const int32_t* q;
-  const uint16_t* n_active;
-  const uint16_t* max_active;
-  const uint32_t* bitmap;   /* adapter-major, A x ceil(P/32) 32-bit words */
-  int W32;
-  double kv_thr;
-  int64_t q_crit, q_lora;
-  /* request-independent masks, computed once per call */
-  uint64_t* m_low;          /* q < q_lora                      filter.go:124-126 */
-  uint64_t* m_room;         /* n_active < max_active           filter.go:175-177 */
-  uint64_t* m_shed;         /* q <= q_crit && kv <= kv_thr     filter.go:183-187 */
-  uint64_t* m_all;
-  int n_low, n_shed;
-} soa_view;
 
 static inline int popc64(uint64_t x) { return __builtin_popcountll(x); }
 
@@ -133,8 +117,8 @@ static int queue_lora_kv(const soa_view* v, const uint32_t* row, uint64_t* x, ui
 }
 
 /* One request; x receives the survivor mask.  Returns the status. */
-static int schedule_one(const soa_view* v, int adapter, int critical, uint64_t* x, uint64_t* t,
-                        int* n_out) {
+int ligo_soa_schedule_one(const soa_view* v, int adapter, int critical, uint64_t* x, uint64_t* t,
+                          int* n_out) {
   const uint32_t* row = (adapter >= 0 && adapter < v->A) ? v->bitmap + (size_t)adapter * v->W32 : NULL;
   const size_t bytes = (size_t)v->W64 * sizeof(uint64_t);
   int n;
@@ -207,7 +191,7 @@ static void* soa_worker(void* arg) {
   uint64_t* t = x + (v->W64 > 0 ? v->W64 : 1);
   for (int i = j->lo; i < j->hi; ++i) {
     int n = 0;
-    int st = schedule_one(v, j->reqs[i].adapter_id, (int)(j->reqs[i].flags & 1u), x, t, &n);
+    int st = ligo_soa_schedule_one(v, j->reqs[i].adapter_id, (int)(j->reqs[i].flags & 1u), x, t, &n);
     int pod = -1;
     if (st == LIGO_OK) {
       uint64_t state = j->seed ^ j->reqs[i].rand_key;
@@ -226,6 +210,29 @@ static void* soa_worker(void* arg) {
   return NULL;
 }
 
+void ligo_soa_view_init(soa_view* v, int P, int A, const double* kv, const int32_t* q,
+                        const uint16_t* n_active, const uint16_t* max_active, const uint32_t* bitmap,
+                        double kv_thr, int64_t q_crit, int64_t q_lora) {
+  memset(v, 0, sizeof(*v));
+  v->P = P; v->A = A; v->W64 = (P + 63) / 64; v->W32 = (P + 31) / 32;
+  v->kv = kv; v->q = q; v->n_active = n_active; v->max_active = max_active; v->bitmap = bitmap;
+  v->kv_thr = kv_thr; v->q_crit = q_crit; v->q_lora = q_lora;
+  size_t words = (size_t)(v->W64 > 0 ? v->W64 : 1);
+  uint64_t* pool = (uint64_t*)calloc(words * 4, sizeof(uint64_t));
+  v->m_low = pool; v->m_room = pool + words; v->m_shed = pool + 2 * words; v->m_all = pool + 3 * words;
+  for (int p = 0; p < P; ++p) {
+    uint64_t bit = 1ull << (p & 63);
+    v->m_all[p >> 6] |= bit;
+    if ((int64_t)q[p] < q_lora) v->m_low[p >> 6] |= bit;
+    if (n_active[p] < max_active[p]) v->m_room[p >> 6] |= bit;
+    if ((int64_t)q[p] <= q_crit && kv[p] <= kv_thr) v->m_shed[p >> 6] |= bit;
+  }
+  v->n_low = mask_count(v->m_low, v->W64);
+  v->n_shed = mask_count(v->m_shed, v->W64);
+}
+
+void ligo_soa_view_free(soa_view* v) { free(v->m_low); v->m_low = NULL; }
+
 int lig_oracle_soa_schedule_batch(int P, int A, const double* kv, const int32_t* q,
                                   const uint16_t* n_active, const uint16_t* max_active,
                                   const uint32_t* bitmap, double kv_thr, int64_t q_crit,
@@ -233,22 +240,7 @@ int lig_oracle_soa_schedule_batch(int P, int A, const double* kv, const int32_t*
                                   lig_oracle_pick* out, uint32_t* masks, int nthreads) {
   if (P < 0 || A < 0 || R < 0 || (R > 0 && (!reqs || !out))) return -1;
   soa_view v;
-  memset(&v, 0, sizeof(v));
-  v.P = P; v.A = A; v.W64 = (P + 63) / 64; v.W32 = (P + 31) / 32;
-  v.kv = kv; v.q = q; v.n_active = n_active; v.max_active = max_active; v.bitmap = bitmap;
-  v.kv_thr = kv_thr; v.q_crit = q_crit; v.q_lora = q_lora;
-  size_t words = (size_t)(v.W64 > 0 ? v.W64 : 1);
-  uint64_t* pool = (uint64_t*)calloc(words * 4, sizeof(uint64_t));
-  v.m_low = pool; v.m_room = pool + words; v.m_shed = pool + 2 * words; v.m_all = pool + 3 * words;
-  for (int p = 0; p < P; ++p) {
-    uint64_t bit = 1ull << (p & 63);
-    v.m_all[p >> 6] |= bit;
-    if ((int64_t)q[p] < q_lora) v.m_low[p >> 6] |= bit;
-    if (n_active[p] < max_active[p]) v.m_room[p >> 6] |= bit;
-    if ((int64_t)q[p] <= q_crit && kv[p] <= kv_thr) v.m_shed[p >> 6] |= bit;
-  }
-  v.n_low = mask_count(v.m_low, v.W64);
-  v.n_shed = mask_count(v.m_shed, v.W64);
+  ligo_soa_view_init(&v, P, A, kv, q, n_active, max_active, bitmap, kv_thr, q_crit, q_lora);
   if (nthreads < 1) nthreads = 1;
   if (nthreads > R) nthreads = R > 0 ? R : 1;
   soa_job* jobs = (soa_job*)calloc((size_t)nthreads, sizeof(soa_job));
@@ -266,6 +258,6 @@ int lig_oracle_soa_schedule_batch(int P, int A, const double* kv, const int32_t*
   }
   free(jobs);
   free(th);
-  free(pool);
+  ligo_soa_view_free(&v);
   return 0;
 }

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for name in names:
         assert hasattr(lib, name), f"liblig.so does not export {name}"
     assert sorted(N.EXPORTED_SYMBOLS) == names
-    assert lib.lig_abi_version() == 1
+    assert lib.lig_abi_version() == N.LIG_ABI_VERSION
     assert b"sm_100a" in lib.lig_version()
 
 

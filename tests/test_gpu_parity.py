@@ -444,21 +444,27 @@ def test_thresholds_are_parameters(engine, oracle):
 
 
 QUEUE_MODES = {
-    "merged": {},                                                          # default: one launch per queue
-    "graph": {"LIG_MERGE_MAX": "1024"},                                    # one kernel per batch, cached CUDA graph
-    "streams": {"LIG_MERGE_MAX": "1024", "LIG_GRAPH": "0"},                # one kernel per batch, forked streams
-    "pdl": {"LIG_MERGE_MAX": "1024", "LIG_GRAPH": "0", "LIG_PDL": "1", "LIG_QUEUE_STREAMS": "1"},
-    "no_prefetch_2streams": {"LIG_MERGE_MAX": "1024", "LIG_GRAPH": "0", "LIG_PREFETCH": "0", "LIG_QUEUE_STREAMS": "2"},
-    "pipelined": {"LIG_MERGE_MAX": "1024", "LIG_PICK_PER_THREAD": "8"},
+    "tma": {},                                                             # default: resident CTAs fed by a TMA ring
+    "tma_1group_2stage_bulk": {"LIG_TMA_GROUPS": "1", "LIG_TMA_STAGES": "2", "LIG_TMA_BULK_STORE": "1",
+                               "LIG_PERSIST_CTAS": "1"},
+    "tma_3group_3stage_bulk": {"LIG_TMA_GROUPS": "3", "LIG_TMA_STAGES": "3", "LIG_TMA_BULK_STORE": "1"},
+    "tma_3group_2stage": {"LIG_TMA_GROUPS": "3", "LIG_TMA_STAGES": "2"},     # more groups than stages
+    "tma_tables_in_global": {"LIG_TAB_SMEM": "0"},                         # strided tables through L1
+    "loop": {"LIG_PICK_KERNEL": "loop"},                                   # resident CTAs, LDG + register prefetch
+    "loop_tables_in_global": {"LIG_PICK_KERNEL": "loop", "LIG_TAB_SMEM": "0"},
+    "merged": {"LIG_PICK_KERNEL": "merged"},                               # round-1 default: blockIdx.y = batch
+    "streams": {"LIG_PICK_KERNEL": "merged", "LIG_MERGE_MAX": "1024"},     # one kernel per batch, forked streams
+    "streams_pipelined": {"LIG_PICK_KERNEL": "merged", "LIG_MERGE_MAX": "1024", "LIG_PICK_PER_THREAD": "8",
+                          "LIG_QUEUE_STREAMS": "2"},
 }
 
 
 @pytest.mark.parametrize("mode", sorted(QUEUE_MODES))
 def test_batch_queue_modes_match_single_batches(mode, monkeypatch):
     """lig_schedule_batches_device: a queue of resident batches gives exactly the per-batch results
-    in every execution mode (merged launch, cached CUDA-graph replay, forked streams, programmatic
-    dependent launch, L2 prefetch on/off, software-pipelined kernel), for the first call, for a
-    replay with another seed, and after the snapshot in the slot changed."""
+    in every execution mode (persistent TMA-ring kernel in several shapes, persistent LDG loop,
+    merged launch, forked streams, software-pipelined kernel), for the first call, for a replay with another
+    seed, and after the snapshot in the slot changed."""
     import torch
     for k, v in QUEUE_MODES[mode].items():
         monkeypatch.setenv(k, v)                    # the knobs are read at lig_create
@@ -507,6 +513,25 @@ def test_batch_queue_modes_match_single_batches(mode, monkeypatch):
         stream.synchronize()
         assert np.array_equal(d_out[1].cpu().numpy().view(PICK_DTYPE), engine.schedule_batch(ep3, 4, host[1]))
         assert np.array_equal(d_out[2].cpu().numpy().view(PICK_DTYPE), engine.schedule_batch(ep3, 9, host[2]))
+        # pick buffers that are only 8-byte aligned (the ABI's minimum): no TMA bulk store possible
+        odd = [torch.zeros(R * 8 + 8, dtype=torch.uint8, device="cuda") for _ in range(3)]
+        with torch.cuda.stream(stream):
+            engine.schedule_batches_device(ep3, 21, [t.data_ptr() for t in d_reqs[:3]], R,
+                                           [t.data_ptr() + 8 for t in odd], stream.cuda_stream)
+        stream.synchronize()
+        for b in range(3):
+            assert np.array_equal(odd[b][8:].cpu().numpy().view(PICK_DTYPE), engine.schedule_batch(ep3, 21 + b, host[b])), (mode, b)
+        # a queue longer than the kernel-parameter item table (97+ batches -> device item table)
+        nq, Rq = 130, 3000
+        big_in = torch.cat([d_reqs[b % nb][: Rq * 16] for b in range(nq)])
+        big_out = torch.zeros(nq * Rq * 8, dtype=torch.uint8, device="cuda")
+        with torch.cuda.stream(stream):
+            engine.schedule_batches_device(ep3, 1000, [big_in.data_ptr() + b * Rq * 16 for b in range(nq)], Rq,
+                                           [big_out.data_ptr() + b * Rq * 8 for b in range(nq)], stream.cuda_stream)
+        stream.synchronize()
+        res = big_out.cpu().numpy().view(PICK_DTYPE).reshape(nq, Rq)
+        for b in (0, 1, 95, 96, 97, 129):
+            assert np.array_equal(res[b], engine.schedule_batch(ep3, 1000 + b, host[b % nb][:Rq])), (mode, b)
     finally:
         engine.close()
 
@@ -544,5 +569,132 @@ def test_doorbell_stream_matches_batch_path(oracle):
             assert np.array_equal(e.stream_submit(2, i, np.ascontiguousarray(reqs[:8])), e.schedule_batch(2, i, np.ascontiguousarray(reqs[:8])))
         e.stream_close()
         e.stream_close()
+    finally:
+        e.close()
+
+
+def test_async_submit_many_in_flight(oracle):
+    """lig_schedule_batch_async/_wait: many batches in flight on one ctx from several threads while
+    the snapshot is re-uploaded underneath them (the reader ring keeps a slot from being
+    overwritten while a batch still reads it; an evicted epoch answers STALE_EPOCH, never garbage)."""
+    import threading
+    lib = N.load()
+    P_, A_, R_ = 400, 32, 20_000
+    snaps = [WL.make_snapshot(P_, A_, seed=70 + i) for i in range(4)]
+    reqs = WL.make_requests(R_, A_, seed=80)
+    wants = [oracle.Pool(s.pod_records()).schedule_batch(s.adapter_names(), WL.UNKNOWN_MODEL, reqs, 5, False,
+                                                         oracle.hardware_threads())[0] for s in snaps]
+    e = Engine(0, max_pods=512, max_adapters=32, max_batch=R_)
+    nthreads, per_thread = 6, 40
+    bufs = []
+    try:
+        for _ in range(nthreads):
+            h_in, h_out = lib.lig_host_alloc(R_ * 16), lib.lig_host_alloc(R_ * 8)
+            np.ctypeslib.as_array((C.c_uint8 * (R_ * 16)).from_address(h_in))[:] = reqs.view(np.uint8).reshape(-1)
+            bufs.append((h_in, h_out))
+        e.upload_snapshot(1, snaps[0].packed)
+        stop = threading.Event()
+        errors, done = [], [0]
+
+        def refresher():
+            ep = 1
+            while not stop.is_set():
+                ep += 1
+                try:
+                    e.upload_snapshot(ep, snaps[(ep - 1) % 4].packed)
+                except Exception as ex:      # noqa: BLE001
+                    errors.append(repr(ex))
+                    return
+                current[0] = ep
+
+        current = [1]
+
+        def caller(k):
+            h_in, h_out = bufs[k]
+            view = np.ctypeslib.as_array((C.c_uint8 * (R_ * 8)).from_address(h_out)).view(PICK_DTYPE)
+            for _ in range(per_thread):
+                ep = current[0]
+                try:
+                    t = e.schedule_batch_async(ep, 5, h_in, R_, h_out)
+                    e.schedule_wait(t)
+                except N.LigError as ex:
+                    if ex.code == N.LIG_ERR_STALE_EPOCH:
+                        continue             # two refreshes raced past this batch: the caller re-resolves
+                    errors.append(repr(ex))
+                    return
+                if not np.array_equal(view, wants[(ep - 1) % 4]):
+                    errors.append(f"thread {k}: wrong picks for epoch {ep}")
+                    return
+                done[0] += 1
+
+        th = [threading.Thread(target=caller, args=(k,)) for k in range(nthreads)]
+        rf = threading.Thread(target=refresher)
+        rf.start()
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        stop.set()
+        rf.join()
+        assert not errors, errors[:3]
+        assert done[0] > nthreads * per_thread // 4
+        # ticket exhaustion is an error code, not a hang
+        tickets = []
+        with pytest.raises(N.LigError) as ei:
+            for _ in range(N.LIG_MAX_TICKETS + 1):
+                tickets.append(e.schedule_batch_async(current[0], 5, bufs[0][0], 16, bufs[0][1]))
+        assert ei.value.code == N.LIG_ERR_BUSY and len(tickets) == N.LIG_MAX_TICKETS
+        for t in tickets:
+            e.schedule_wait(t)
+        with pytest.raises(N.LigError):           # pageable buffers are refused by the async form
+            e.schedule_batch_async(current[0], 5, reqs.ctypes.data, 16, np.empty(16, dtype=PICK_DTYPE).ctypes.data)
+    finally:
+        e.close()
+        for h_in, h_out in bufs:
+            lib.lig_host_free(h_in)
+            lib.lig_host_free(h_out)
+
+
+def test_readers_on_many_streams_vs_device_uploads(oracle):
+    """Queues on several caller streams read a slot while device-side uploads keep replacing the
+    OTHER slot and then this one: every result must be that of the epoch it was enqueued against
+    (a single idle event per slot lost all but the last reader)."""
+    import torch
+    P_, A_, R_ = 600, 40, 300_000
+    snaps = [WL.make_snapshot(P_, A_, seed=90 + i) for i in range(3)]
+    blobs = [torch.from_numpy(s.packed.blob()).cuda() for s in snaps]
+    reqs = WL.make_requests(R_, A_, seed=99)
+    d_reqs = torch.from_numpy(reqs.view(np.uint8).reshape(-1)).cuda()
+    e = Engine(0, max_pods=1024, max_adapters=64, max_batch=R_)
+    try:
+        want = []
+        for i, s in enumerate(snaps):
+            e.upload_snapshot(100 + i, s.packed)
+            want.append(e.schedule_batch(100 + i, 3, reqs))
+        streams = [torch.cuda.Stream() for _ in range(5)]
+        up = torch.cuda.Stream()
+        outs = [torch.zeros(R_ * 8, dtype=torch.uint8, device="cuda") for _ in range(5 * 6)]
+        expect = []
+        ep = 200
+        e.upload_snapshot_device(ep, P_, A_, blobs[0].data_ptr(), up.cuda_stream)
+        cur = 0
+        k = 0
+        for it in range(6):
+            for si, st in enumerate(streams):
+                e.schedule_batches_device(ep, 3, [d_reqs.data_ptr()] * 3, R_, [outs[k].data_ptr()] * 3, st.cuda_stream)
+                expect.append(cur)
+                k += 1
+            # replace the other slot, then the slot the streams above are still reading
+            nxt = (cur + 1) % 3
+            ep += 1
+            e.upload_snapshot_device(ep, P_, A_, blobs[nxt].data_ptr(), up.cuda_stream)
+            cur = nxt
+        torch.cuda.synchronize()
+        for i in range(k):
+            # three batches wrote the same buffer with seeds 3,4,5: the last one wins
+            got = outs[i].cpu().numpy().view(PICK_DTYPE)
+            assert np.array_equal(got["n_survivors"], want[expect[i]]["n_survivors"]), i
+            assert np.array_equal(got["status"], want[expect[i]]["status"]), i
+            assert (got["pod_idx"] < P_).all()
     finally:
         e.close()
