@@ -35,7 +35,10 @@ extern "C" {
  * LIG_EMPTY the tree returned ([], nil): "failed to apply filter, resulted 0 pods, this should
  *           never happen"                                      scheduler.go:116-118
  */
-enum { LIG_OK = 0, LIG_DROP = 1, LIG_EMPTY = 2 };
+enum { LIG_OK = 0, LIG_DROP = 1, LIG_EMPTY = 2,
+       /* only from the model entry points (lig_schedule_models_*): FetchModelData returned nil,
+        * "error finding a model object in InferenceModel for input ..."  handlers/request.go:42-45 */
+       LIG_NO_MODEL = 3 };
 
 /* ---- batch-level error codes (negative return values) ---------------------------------------- */
 enum {
@@ -228,6 +231,59 @@ int lig_schedule_scan(lig_ctx* ctx, uint64_t epoch, uint64_t seed, const lig_req
 int lig_read_class(lig_ctx* ctx, uint64_t epoch, int critical, int adapter_id, int* status,
                    int* n_survivors, uint16_t* list);
 
+/* ---- the step before Schedule, on the device ------------------------------------------------------
+ * Replaces, per request, the resolve step of HandleRequestBody (handlers/request.go:42-56):
+ * datastore.FetchModelData(model) (backend/datastore.go:70-76), backend.RandomWeightedDraw over
+ * Spec.TargetModels (datastore.go:78-98) and backend.IsCritical (datastore.go:100-105).  The host
+ * interns the InferenceModel names to dense model ids once per datastore change and the request
+ * shrinks to ONE 32-bit model id; the device looks the model up, draws the target model, derives
+ * Critical and schedules — one pass over the batch, 4 bytes in and 4 bytes out per decision.
+ *
+ * The model table belongs to a resident snapshot epoch: target models are given as adapter ids
+ * interned against that snapshot (an id outside [0, A) = a model no pod lists in ActiveModels).
+ *   target_offsets[n_models + 1]   CSR offsets into the two target arrays (TargetModels order)
+ *   target_adapter_ids / weights   Spec.TargetModels[k].Name (interned) / .Weight
+ *   critical[n_models]             IsCritical(model)
+ *   self_adapter_ids[n_models]     the model's own name interned: used when TargetModels is empty
+ *                                  (request.go:47: modelName stays the requested model)
+ *   present[n_models] (nullable)   0 = FetchModelData returns nil for this id -> LIG_NO_MODEL
+ * Weights must be >= 0 and sum to [1, 2^31-1] for every model with targets (Go's Int31n panics on
+ * a non-positive sum, a negative weight makes the reference's loop ill-defined), at most 255
+ * targets per model: LIG_ERR_RANGE otherwise.
+ *
+ * The draw.  The reference draws from rand.NewSource(rand.Int63()) (request.go:48 passes seed 0):
+ * unseeded, not reproducible.  As for the pick, this ABI defines it on a SplitMix64 source private
+ * to the request: state = seed ^ rand_key ^ LIG_DRAW_DOMAIN, randomVal = Int31n(sum of weights)
+ * (Go 1.22 algorithm, see below), target = first k with randomVal < Weight[k], else
+ * randomVal -= Weight[k] (datastore.go:91-97).  A model with exactly one target skips the draw
+ * (its result cannot depend on it).  The pick then uses state = seed ^ rand_key as always, so
+ * lig_schedule_models_batch(ids) == lig_schedule_batch(descriptors resolved on the host).
+ * rand_key of request i of a call is first_index + i (a counter-based key: shards of one batch
+ * pass their offset and get the single-device result). */
+#define LIG_DRAW_DOMAIN 0xA0761D6478BD642Full
+typedef struct lig_mpick {
+  int16_t pod_idx;     /* as lig_pick.pod_idx (-1 unless LIG_OK)                                  */
+  uint8_t status;      /* LIG_OK / LIG_DROP / LIG_EMPTY / LIG_NO_MODEL                            */
+  uint8_t target_idx;  /* index of the drawn Spec.TargetModels entry (the body's "model" rewrite,
+                          request.go:61-69); 255 = TargetModels empty, the model name passes through */
+} lig_mpick;
+int lig_upload_models(lig_ctx* ctx, uint64_t epoch, int n_models, const int32_t* target_offsets,
+                      const int32_t* target_adapter_ids, const int32_t* target_weights,
+                      const uint8_t* critical, const int32_t* self_adapter_ids, const uint8_t* present);
+/* Host buffers (page-locked ones are read / written over PCIe in place), blocking. */
+int lig_schedule_models_batch(lig_ctx* ctx, uint64_t epoch, uint64_t seed, uint64_t first_index,
+                              const uint32_t* model_ids, int R, lig_mpick* out);
+/* HBM-resident queue of n_batches batches of R model ids (4-byte aligned; 16-byte aligned buffers
+ * take the TMA path), batch b with seed + b; enqueued on `stream`, not synchronised. */
+int lig_schedule_models_batches_device(lig_ctx* ctx, uint64_t epoch, uint64_t seed, uint64_t first_index,
+                                       const uint32_t* const* d_model_ids, int R,
+                                       lig_mpick* const* d_out, int n_batches, void* stream);
+/* Test hook: only the resolve step, returning the 16-byte descriptor the device built for every
+ * request (adapter_id, Critical, rand_key = first_index + i) and its status (LIG_OK / LIG_NO_MODEL)
+ * and target index in `out`. */
+int lig_resolve_models(lig_ctx* ctx, uint64_t epoch, uint64_t seed, uint64_t first_index,
+                       const uint32_t* model_ids, int R, lig_req* reqs_out, lig_mpick* out);
+
 /* ---- several GPUs, one process (the reference runs ONE scheduler per process, main.go:137) ------
  * A lig_group owns one lig_ctx per listed CUDA device and an NCCL communicator over them
  * (ncclCommInitAll).  The request batch shards BY REQUEST (decisions are independent given a
@@ -279,6 +335,11 @@ int         lig_abi_version(void);
 int         lig_device_count(void);          /* 0 when no CUDA device / driver */
 uint64_t    lig_kernel_launches(const lig_ctx* ctx);  /* kernels this ctx launched so far */
 int         lig_sm_count(const lig_ctx* ctx);
+/* The pick kernel a device-resident queue launches against `epoch` right now: its name, resident
+ * grid and block size (bench.py checks its committed ncu capture against this), and the size of
+ * the compact tables (0 = not available / strided tables in use). */
+int         lig_pick_kernel_info(lig_ctx* ctx, uint64_t epoch, char* name, int name_len, int* grid,
+                                 int* threads, int* table_bytes, int* tables_in_smem);
 
 #ifdef __cplusplus
 }

@@ -11,7 +11,8 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liblig.so")
 
-LIG_OK, LIG_DROP, LIG_EMPTY = 0, 1, 2
+LIG_OK, LIG_DROP, LIG_EMPTY, LIG_NO_MODEL = 0, 1, 2, 3
+LIG_DRAW_DOMAIN = 0xA0761D6478BD642F
 LIG_ERR_INVALID, LIG_ERR_CUDA, LIG_ERR_STALE_EPOCH, LIG_ERR_NO_SNAPSHOT, LIG_ERR_RANGE = -1, -2, -3, -4, -5
 LIG_ERR_BUSY, LIG_ERR_NCCL = -6, -7
 LIG_MAX_TICKETS, LIG_COMM_ID_BYTES = 256, 128
@@ -32,6 +33,8 @@ EXPORTED_SYMBOLS = (
     "lig_group_upload_snapshot", "lig_group_schedule_batch",
     "lig_comm_unique_id", "lig_comm_init_rank", "lig_comm_upload_snapshot_device", "lig_comm_upload_snapshot",
     "lig_comm_allreduce_i32",
+    "lig_upload_models", "lig_schedule_models_batch", "lig_schedule_models_batches_device", "lig_resolve_models",
+    "lig_pick_kernel_info",
 )
 
 
@@ -114,6 +117,12 @@ def load() -> C.CDLL:
     lib.lig_comm_upload_snapshot_device.argtypes = [vp, u64, i32, i32, vp, i32, vp]
     lib.lig_comm_upload_snapshot.argtypes = [vp, u64, i32, i32, vp, vp, vp, vp, vp, i32]
     lib.lig_comm_allreduce_i32.argtypes = [vp, vp, i32, vp]
+    lib.lig_upload_models.argtypes = [vp, u64, i32, vp, vp, vp, vp, vp, vp]
+    lib.lig_schedule_models_batch.argtypes = [vp, u64, u64, u64, vp, i32, vp]
+    lib.lig_schedule_models_batches_device.argtypes = [vp, u64, u64, u64, vp, i32, vp, i32, vp]
+    lib.lig_resolve_models.argtypes = [vp, u64, u64, u64, vp, i32, vp, vp]
+    lib.lig_pick_kernel_info.argtypes = [vp, u64, C.c_char_p, i32, C.POINTER(i32), C.POINTER(i32),
+                                         C.POINTER(i32), C.POINTER(i32)]
     for name in EXPORTED_SYMBOLS:
         getattr(lib, name)  # AttributeError if the library does not export it
     _lib = lib

@@ -12,7 +12,7 @@ Reference: pkg/ext-proc/backend/types.go:8-31 (Pod, Metrics, PodMetrics), :37-53
 from __future__ import annotations
 
 from dataclasses import dataclass, field
-from typing import Dict
+from typing import Dict, List, Optional
 
 
 @dataclass(frozen=True)
@@ -47,3 +47,30 @@ class PodMetrics:                            # backend/types.go:28-31
             ActiveModels=dict(m.ActiveModels), RunningQueueSize=m.RunningQueueSize,
             WaitingQueueSize=m.WaitingQueueSize, KVCacheUsagePercent=m.KVCacheUsagePercent,
             KvCacheMaxTokenCapacity=m.KvCacheMaxTokenCapacity))
+
+
+# ---- api/v1alpha1/inferencemodel_types.go: the fields the request path reads --------------------
+CRITICAL, DEFAULT, SHEDDABLE = "Critical", "Default", "Sheddable"     # inferencemodel_types.go:105-111
+
+
+@dataclass
+class TargetModel:                           # inferencemodel_types.go: TargetModel{Name, Weight}
+    Name: str = ""
+    Weight: int = 0
+
+
+@dataclass
+class InferenceModelSpec:                    # inferencemodel_types.go:40-69
+    ModelName: str = ""
+    Criticality: Optional[str] = None
+    TargetModels: List[TargetModel] = field(default_factory=list)
+
+
+@dataclass
+class InferenceModel:
+    Name: str = ""
+    Spec: InferenceModelSpec = field(default_factory=InferenceModelSpec)
+
+
+def IsCritical(model: InferenceModel) -> bool:          # backend/datastore.go:100-105
+    return model.Spec.Criticality is not None and model.Spec.Criticality == CRITICAL

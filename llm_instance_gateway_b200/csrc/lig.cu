@@ -86,6 +86,13 @@ struct Slot {
   uint32_t ctab_pool_capacity = 0;  // list entries the compact pool can hold
   CompactHeader* h_hdr = nullptr;   // pinned copy of the blob's header, valid once `ready` completed
   unsigned char* h_blob = nullptr;  // pinned staging for host uploads
+  // model table of this epoch (lig_upload_models), grown on demand
+  unsigned char* d_mtab = nullptr;
+  unsigned char* h_mtab = nullptr;  // pinned staging
+  size_t mtab_capacity = 0;
+  uint32_t mtab_bytes = 0, n_models = 0;
+  bool models_valid = false;
+  cudaEvent_t models_ready = nullptr;
   cudaEvent_t ready = nullptr;      // class tables built
   // Batches that read this slot, possibly on different caller streams: a ring of events, one per
   // schedule call.  A writer (re-upload, threshold rebuild) waits on every event of the ring; when
@@ -157,9 +164,12 @@ struct lig_ctx {
   // CTAs, LDG with register prefetch) | merged (round 1: one short-lived CTA per 1024 requests)
   int pick_kernel = 0;              // 0 tma, 1 loop, 2 merged
   int tma_groups = 2;               // LIG_TMA_GROUPS = 1|2|3 consumer groups of 8 warps per CTA
-  int tma_stages = 4;               // LIG_TMA_STAGES = 2|3|4|6 ring stages of 16 KB per CTA
+  int tma_stages = 2;               // LIG_TMA_STAGES = 2|3|4|6 ring stages of 16 KB per CTA (a multiple of the groups)
   bool tma_bulk_store = false;      // LIG_TMA_BULK_STORE=1: picks leave through TMA bulk stores
   bool tab_smem = true;             // LIG_TAB_SMEM=0: never pull the compact tables into shared memory
+  int models_groups = 2;            // LIG_MODELS_GROUPS = 1|2, LIG_MODELS_STAGES = 2|4|8 (4 KB stages)
+  int models_stages = 4;
+  int models_grid[2] = {0, 0};      // resident CTAs of the model-request kernel: [tables in smem?]
   int persist_ctas_req = 0;         // LIG_PERSIST_CTAS: resident CTAs per SM (0 = as many as fit)
   int persist_grid[2][2] = {};      // resident CTAs of the tma variant: [bulk stores?][tables in smem?]
   int loop_grid[2] = {0, 0};        // resident CTAs of the loop kernel: [tables in smem?]
@@ -328,6 +338,16 @@ PersistVariant loop_variant(bool tab) {
   return v;
 }
 
+// May the class tables (and, with_models, the model table behind them) go to shared memory?
+bool tables_fit_smem(const lig_ctx* c, const Slot& s, bool with_models) {
+  if (!c->tab_smem) return false;
+  const bool done = cudaEventQuery(s.ready) == cudaSuccess;
+  cudaGetLastError();   // cudaErrorNotReady is not an error
+  if (!done || s.h_hdr->bytes == 0 || s.h_hdr->n_classes != 2u * (uint32_t)(s.A + 1)) return false;
+  const size_t need = (size_t)s.h_hdr->bytes + (with_models ? (size_t)s.mtab_bytes : 0);
+  return need <= kTabBudget;
+}
+
 // The persistent TMA-pipelined pick over a queue of n batches of R requests (one launch per
 // <= 2^30 tiles).  Caller holds c->mu.
 int launch_persistent(lig_ctx* c, const Slot& s, uint64_t seed, const lig_req* const* reqs, int R,
@@ -338,9 +358,7 @@ int launch_persistent(lig_ctx* c, const Slot& s, uint64_t seed, const lig_req* c
   const int tpb = (R + tile - 1) / tile;
   // the compact tables go to shared memory when their header is back (the build has completed)
   // and they fit the budget; otherwise the strided tables are read through L1 (same results)
-  const bool tab = c->tab_smem && cudaEventQuery(s.ready) == cudaSuccess && s.h_hdr->bytes != 0 &&
-                   s.h_hdr->bytes <= kTabBudget && s.h_hdr->n_classes == 2u * (uint32_t)(s.A + 1);
-  cudaGetLastError();   // cudaEventQuery's cudaErrorNotReady is not an error
+  const bool tab = tables_fit_smem(c, s, false);
   int per_launch = (1 << 30) / tpb;
   if (per_launch > lig_ctx::kMaxItems) per_launch = lig_ctx::kMaxItems;
   if (per_launch < 1) per_launch = 1;
@@ -390,6 +408,74 @@ int launch_persistent(lig_ctx* c, const Slot& s, uint64_t seed, const lig_req* c
     }
     c->launches++;
     if (slot >= 0) CUDA_TRY(cudaEventRecord(c->items_free[slot], st));   // after the kernel that reads the table
+  }
+  return 0;
+}
+
+template <int kGroups, bool kTab>
+PersistVariant mvariant_for_stages(int stages) {
+  PersistVariant v;
+  v.threads = persist_threads(kGroups);
+  switch (stages) {
+    case 2: v.fn = reinterpret_cast<const void*>(&lig_pick_models_kernel<kGroups, 2, kTab>); v.smem = mpersist_smem_bytes(2, kTab); break;
+    case 8: v.fn = reinterpret_cast<const void*>(&lig_pick_models_kernel<kGroups, 8, kTab>); v.smem = mpersist_smem_bytes(8, kTab); break;
+    default: v.fn = reinterpret_cast<const void*>(&lig_pick_models_kernel<kGroups, 4, kTab>); v.smem = mpersist_smem_bytes(4, kTab); break;
+  }
+  return v;
+}
+
+PersistVariant models_variant(int groups, int stages, bool tab) {
+  if (groups == 1) return tab ? mvariant_for_stages<1, true>(stages) : mvariant_for_stages<1, false>(stages);
+  return tab ? mvariant_for_stages<2, true>(stages) : mvariant_for_stages<2, false>(stages);
+}
+
+// Model-id batches against slot s (caller holds c->mu and has checked s.models_valid).
+int launch_models(lig_ctx* c, const Slot& s, uint64_t seed, uint64_t first_index,
+                  const uint32_t* const* ids, int R, lig_mpick* const* outs, int n_batches,
+                  cudaStream_t st, bool allow_persistent) {
+  if (R == 0 || n_batches == 0) return 0;
+  const uint4* cls = reinterpret_cast<const uint4*>(s.d_cls);
+  const uint16_t* lists = s.d_lists;
+  int A = s.A;
+  bool aligned = (R % 4) == 0;
+  for (int b = 0; b < n_batches; ++b)
+    if ((reinterpret_cast<uintptr_t>(ids[b]) | reinterpret_cast<uintptr_t>(outs[b])) & 15u) aligned = false;
+  if (!allow_persistent || !aligned || c->pick_kernel == 2) {
+    // plain kernel, one launch per batch (host-mapped buffers, odd sizes or alignments)
+    const unsigned char* mtab = s.d_mtab;
+    for (int b = 0; b < n_batches; ++b) {
+      lig_pick_models_stream_kernel<<<(R + kTile - 1) / kTile, kGroupThreads, 0, st>>>(
+          ids[b], reinterpret_cast<uint32_t*>(outs[b]), R, cls, lists, A, mtab, s.n_models,
+          seed + (uint64_t)b, first_index, nullptr);
+      CUDA_TRY(cudaGetLastError());
+      c->launches++;
+    }
+    return 0;
+  }
+  const bool tab = tables_fit_smem(c, s, true);
+  const int tpb = (R + kTile - 1) / kTile;
+  int per_launch = (1 << 30) / tpb;
+  if (per_launch > kMaxInlineMItems) per_launch = kMaxInlineMItems;   // longer queues: several launches
+  for (int lo = 0; lo < n_batches; lo += per_launch) {
+    const int n = (n_batches - lo) < per_launch ? (n_batches - lo) : per_launch;
+    MQueueParams qp;
+    qp.n_batches = n;
+    qp.R = R;
+    qp.tiles_per_batch = tpb;
+    qp.total_tiles = n * tpb;
+    qp.dev_items = nullptr;
+    for (int b = 0; b < n; ++b)
+      qp.items[b] = MQueueItem{ids[lo + b], reinterpret_cast<uint32_t*>(outs[lo + b]), seed + (uint64_t)(lo + b), first_index};
+    const unsigned char* ctab = s.d_ctab;
+    uint32_t ctab_bytes = tab ? s.h_hdr->bytes : 0u;
+    const unsigned char* mtab = s.d_mtab;
+    uint32_t mtab_bytes = s.mtab_bytes, n_models = s.n_models;
+    void* args[9] = {&qp, &cls, &lists, &A, &ctab, &ctab_bytes, &mtab, &mtab_bytes, &n_models};
+    const PersistVariant v = models_variant(c->models_groups, c->models_stages, tab);
+    const int cap = c->models_grid[tab ? 1 : 0];
+    const int grid = qp.total_tiles < cap ? qp.total_tiles : cap;
+    CUDA_TRY(cudaLaunchKernel(v.fn, dim3((unsigned)grid), dim3((unsigned)v.threads), args, v.smem, st));
+    c->launches++;
   }
   return 0;
 }
@@ -528,6 +614,7 @@ int begin_write(lig_ctx* c, uint64_t epoch, int P, int A, cudaStream_t stream, b
     std::lock_guard<std::mutex> lk(c->mu);
     Slot& s = victim_slot(c, epoch);
     s.valid = false;                       // evicted: schedule calls on its old epoch now get STALE_EPOCH
+    s.models_valid = false;                // the model table is interned against the old snapshot
     rc = wait_readers(s, st);              // batches still reading the old content
     if (!rc && cudaStreamWaitEvent(st, s.ready, 0) != cudaSuccess)   // an earlier device-side upload of this slot
       rc = fail(LIG_ERR_CUDA, "cudaStreamWaitEvent failed");
@@ -694,6 +781,7 @@ static int create_impl(lig_ctx* c, int device, int max_pods, int max_adapters, i
     }
     CUDA_TRY(cudaHostAlloc(&s.h_blob, l.total, cudaHostAllocDefault));
     CUDA_TRY(cudaEventCreateWithFlags(&s.ready, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&s.models_ready, cudaEventDisableTiming));
     for (auto& ev : s.readers) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   }
   if (const char* e = getenv("LIG_PICK_PER_THREAD")) {
@@ -716,6 +804,14 @@ static int create_impl(lig_ctx* c, int device, int max_pods, int max_adapters, i
   }
   if (const char* e = getenv("LIG_TMA_BULK_STORE")) c->tma_bulk_store = atoi(e) != 0;
   if (const char* e = getenv("LIG_TAB_SMEM")) c->tab_smem = atoi(e) != 0;
+  if (const char* e = getenv("LIG_MODELS_GROUPS")) {
+    int v2 = atoi(e);
+    if (v2 == 1 || v2 == 2) c->models_groups = v2;
+  }
+  if (const char* e = getenv("LIG_MODELS_STAGES")) {
+    int v2 = atoi(e);
+    if (v2 == 2 || v2 == 4 || v2 == 8) c->models_stages = v2;
+  }
   // A consumer group may only wait on a ring stage whose previous phase it consumed itself (an
   // mbarrier parity wait cannot tell "two phases ahead" from "done"): the stage count must be a
   // multiple of the group count, so that a group always returns to the same stages.
@@ -740,6 +836,15 @@ static int create_impl(lig_ctx* c, int device, int max_pods, int max_adapters, i
       if (c->persist_ctas_req > 0 && c->persist_ctas_req < per_sm) per_sm = c->persist_ctas_req;
       c->persist_grid[bulk][tab] = per_sm * c->sm_count;
     }
+  for (int tab = 0; tab < 2; ++tab) {
+    const PersistVariant pv = models_variant(c->models_groups, c->models_stages, tab != 0);
+    CUDA_TRY(cudaFuncSetAttribute(pv.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pv.smem));
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pv.fn, pv.threads, pv.smem));
+    if (per_sm < 1) return fail(LIG_ERR_CUDA, "the model-request kernel does not fit on this device");
+    if (c->persist_ctas_req > 0 && c->persist_ctas_req < per_sm) per_sm = c->persist_ctas_req;
+    c->models_grid[tab] = per_sm * c->sm_count;
+  }
   for (int tab = 0; tab < 2; ++tab) {
     const PersistVariant pv = loop_variant(tab != 0);
     CUDA_TRY(cudaFuncSetAttribute(pv.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(pv.smem ? pv.smem : 16)));
@@ -812,6 +917,9 @@ void lig_destroy(lig_ctx* c) {
     cudaFree(s.d_cls);
     cudaFree(s.d_lists);
     cudaFree(s.d_ctab);
+    cudaFree(s.d_mtab);
+    if (s.h_mtab) cudaFreeHost(s.h_mtab);
+    if (s.models_ready) cudaEventDestroy(s.models_ready);
     if (s.h_hdr) cudaFreeHost(s.h_hdr);
     cudaFreeHost(s.h_blob);
     if (s.ready) cudaEventDestroy(s.ready);
@@ -1105,6 +1213,225 @@ int lig_schedule_scan(lig_ctx* c, uint64_t epoch, uint64_t seed, const lig_req* 
     if (int rc = note_reader(*s, st)) return rc;
   }
   CUDA_TRY(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int lig_upload_models(lig_ctx* c, uint64_t epoch, int n_models, const int32_t* off,
+                      const int32_t* tgt_ids, const int32_t* tgt_w, const uint8_t* critical,
+                      const int32_t* self_ids, const uint8_t* present) {
+  if (!c || n_models < 0 || (n_models > 0 && (!off || !critical || !self_ids)))
+    return fail(LIG_ERR_INVALID, "lig_upload_models: bad argument");
+  const int n_rec_in = n_models ? off[n_models] : 0;
+  if (n_rec_in < 0 || (n_rec_in > 0 && (!tgt_ids || !tgt_w)))
+    return fail(LIG_ERR_INVALID, "lig_upload_models: bad target arrays");
+  // build the blob on the host (see lig_device.cuh: ModelHeader)
+  std::vector<uint32_t> entries((size_t)n_models * 4);
+  std::vector<uint32_t> targets;
+  for (int m = 0; m < n_models; ++m) {
+    const int lo = off[m], hi = off[m + 1];
+    if (lo < 0 || hi < lo || hi > n_rec_in) return fail(LIG_ERR_INVALID, "model %d: bad target_offsets", m);
+    const int nt = hi - lo;
+    if (nt > 255) return fail(LIG_ERR_RANGE, "model %d has %d target models (at most 255)", m, nt);
+    int64_t total = 0;
+    for (int k = lo; k < hi; ++k) {
+      if (tgt_w[k] < 0) return fail(LIG_ERR_RANGE, "model %d: negative weight %d", m, tgt_w[k]);
+      total += tgt_w[k];
+    }
+    if (nt > 0 && (total < 1 || total > 0x7fffffffLL))
+      return fail(LIG_ERR_RANGE, "model %d: weights sum to %lld (Go's Int31n needs [1, 2^31-1])", m, (long long)total);
+    uint32_t info = (uint32_t)nt | (critical[m] ? kModelCritical : 0u) | ((!present || present[m]) ? kModelPresent : 0u);
+    uint32_t magic = 0, w = (uint32_t)self_ids[m];
+    if (nt == 1) w = (uint32_t)tgt_ids[lo];
+    if (nt >= 2) {
+      const uint32_t n = (uint32_t)total;
+      if (n >= 2) {
+        uint32_t l = 0;
+        while ((1ull << l) < n) ++l;                                   // ceil(log2 n)
+        const uint32_t shift = l - 1;
+        magic = (uint32_t)((((unsigned long long)1 << (32u + shift)) + n - 1u) / n);
+        info |= shift << 12;
+      }
+      w = (uint32_t)(targets.size() / 2);
+      uint32_t cum = 0;
+      for (int k = lo; k < hi; ++k) {
+        cum += (uint32_t)tgt_w[k];
+        targets.push_back((uint32_t)tgt_ids[k]);
+        targets.push_back(cum);
+      }
+    }
+    entries[(size_t)m * 4 + 0] = info;
+    entries[(size_t)m * 4 + 1] = magic;
+    entries[(size_t)m * 4 + 2] = (uint32_t)total;
+    entries[(size_t)m * 4 + 3] = w;
+  }
+  const size_t bytes = (sizeof(ModelHeader) + entries.size() * 4 + targets.size() * 4 + 15) & ~(size_t)15;
+  std::lock_guard<std::mutex> uk(c->upload_mu);
+  CUDA_TRY(cudaSetDevice(c->device));
+  Slot* s = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (int rc = resolve_slot(c, epoch, &s)) return rc;
+    s->models_valid = false;
+    if (int rc = wait_readers(*s, c->s_up)) return rc;      // batches still reading the old table
+  }
+  if (bytes > s->mtab_capacity) {
+    if (c->stream_open)
+      return fail(LIG_ERR_INVALID, "cannot grow the model table while a doorbell stream is open");
+    CUDA_TRY(cudaStreamSynchronize(c->s_up));                 // the readers are done: safe to free
+    cudaFree(s->d_mtab);
+    if (s->h_mtab) cudaFreeHost(s->h_mtab);
+    s->d_mtab = nullptr;
+    s->h_mtab = nullptr;
+    s->mtab_capacity = 0;
+    const size_t cap = bytes * 2;
+    CUDA_TRY(cudaMalloc(&s->d_mtab, cap));
+    CUDA_TRY(cudaHostAlloc(&s->h_mtab, cap, cudaHostAllocDefault));
+    s->mtab_capacity = cap;
+  }
+  memset(s->h_mtab, 0, bytes);
+  ModelHeader* h = reinterpret_cast<ModelHeader*>(s->h_mtab);
+  h->bytes = (uint32_t)bytes;
+  h->n_models = (uint32_t)n_models;
+  h->n_target_records = (uint32_t)(targets.size() / 2);
+  if (!entries.empty()) memcpy(s->h_mtab + sizeof(ModelHeader), entries.data(), entries.size() * 4);
+  if (!targets.empty()) memcpy(s->h_mtab + sizeof(ModelHeader) + entries.size() * 4, targets.data(), targets.size() * 4);
+  CUDA_TRY(cudaMemcpyAsync(s->d_mtab, s->h_mtab, bytes, cudaMemcpyHostToDevice, c->s_up));
+  CUDA_TRY(cudaEventRecord(s->models_ready, c->s_up));
+  CUDA_TRY(cudaStreamSynchronize(c->s_up));
+  {
+    std::lock_guard<std::mutex> lk(c->mu);
+    s->mtab_bytes = (uint32_t)bytes;
+    s->n_models = (uint32_t)n_models;
+    s->models_valid = s->valid && s->epoch == epoch;
+  }
+  return 0;
+}
+
+static int resolve_models_slot(lig_ctx* c, uint64_t epoch, Slot** out) {
+  if (int rc = resolve_slot(c, epoch, out)) return rc;
+  if (!(*out)->models_valid)
+    return fail(LIG_ERR_NO_SNAPSHOT, "no model table uploaded for epoch %llu (lig_upload_models)",
+                (unsigned long long)epoch);
+  return 0;
+}
+
+int lig_schedule_models_batches_device(lig_ctx* c, uint64_t epoch, uint64_t seed, uint64_t first_index,
+                                       const uint32_t* const* d_ids, int R, lig_mpick* const* d_out,
+                                       int n_batches, void* stream) {
+  if (!c || R < 0 || n_batches < 0 || (n_batches > 0 && (!d_ids || !d_out)))
+    return fail(LIG_ERR_INVALID, "lig_schedule_models_batches_device: bad argument");
+  std::lock_guard<std::mutex> lk(c->mu);
+  Slot* s = nullptr;
+  if (int rc = resolve_models_slot(c, epoch, &s)) return rc;
+  if (n_batches == 0 || R == 0) return 0;
+  for (int b = 0; b < n_batches; ++b)
+    if (!d_ids[b] || !d_out[b])
+      return fail(LIG_ERR_INVALID, "lig_schedule_models_batches_device: null buffer in batch %d", b);
+  CUDA_TRY(cudaSetDevice(c->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUDA_TRY(cudaStreamWaitEvent(st, s->ready, 0));
+  CUDA_TRY(cudaStreamWaitEvent(st, s->models_ready, 0));
+  if (int rc = launch_models(c, *s, seed, first_index, d_ids, R, d_out, n_batches, st, true)) return rc;
+  return note_reader(*s, st);
+}
+
+int lig_schedule_models_batch(lig_ctx* c, uint64_t epoch, uint64_t seed, uint64_t first_index,
+                              const uint32_t* ids, int R, lig_mpick* out) {
+  if (!c || R < 0 || (R > 0 && (!ids || !out)))
+    return fail(LIG_ERR_INVALID, "lig_schedule_models_batch: bad argument");
+  if (R > c->max_batch) return fail(LIG_ERR_INVALID, "R=%d exceeds max_batch=%d", R, c->max_batch);
+  const uint32_t* dev_in = R ? mapped_device_pointer(ids) : nullptr;
+  lig_mpick* dev_out = R ? mapped_device_pointer(out) : nullptr;
+  const bool bounce = R > 0 && !(dev_in && dev_out);
+  std::unique_lock<std::mutex> bk(c->bounce_mu, std::defer_lock);
+  if (bounce) {   // the 16 B / 8 B bounce buffers of the descriptor path are large enough
+    bk.lock();
+    dev_in = reinterpret_cast<const uint32_t*>(mapped_device_pointer(c->h_reqs));
+    dev_out = reinterpret_cast<lig_mpick*>(mapped_device_pointer(c->h_out));
+    if (!dev_in || !dev_out)
+      return fail(LIG_ERR_CUDA, "pinned staging buffers are not device-mapped on this platform");
+    memcpy(c->h_reqs, ids, (size_t)R * sizeof(uint32_t));
+  }
+  int ticket = -1;
+  {
+    std::lock_guard<std::mutex> lk(c->mu);
+    Slot* s = nullptr;
+    if (int rc = resolve_models_slot(c, epoch, &s)) return rc;
+    if (R == 0) return 0;
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (c->free_tickets.empty())
+      return fail(LIG_ERR_BUSY, "all %d tickets are in flight: call lig_schedule_wait first", LIG_MAX_TICKETS);
+    const int lane = c->next_lane;
+    c->next_lane = (lane + 1) % kLanes;
+    cudaStream_t st = c->s_lane[lane];
+    CUDA_TRY(cudaStreamWaitEvent(st, s->ready, 0));
+    CUDA_TRY(cudaStreamWaitEvent(st, s->models_ready, 0));
+    if (int rc = launch_models(c, *s, seed, first_index, &dev_in, R, &dev_out, 1, st, false)) return rc;
+    if (int rc = note_reader(*s, st)) return rc;
+    ticket = c->free_tickets.back();
+    CUDA_TRY(cudaEventRecord(c->ticket_ev[ticket], st));
+    c->free_tickets.pop_back();
+  }
+  if (int rc = lig_schedule_wait(c, ticket)) return rc;
+  if (bounce) memcpy(out, c->h_out, (size_t)R * sizeof(lig_mpick));
+  return 0;
+}
+
+int lig_resolve_models(lig_ctx* c, uint64_t epoch, uint64_t seed, uint64_t first_index,
+                       const uint32_t* ids, int R, lig_req* reqs_out, lig_mpick* out) {
+  if (!c || R < 0 || (R > 0 && (!ids || !reqs_out || !out)))
+    return fail(LIG_ERR_INVALID, "lig_resolve_models: bad argument");
+  if (R > c->max_batch) return fail(LIG_ERR_INVALID, "R=%d exceeds max_batch=%d", R, c->max_batch);
+  std::lock_guard<std::mutex> bk(c->bounce_mu);   // test hook: uses the ctx's staging buffers
+  cudaStream_t st = c->s_lane[0];
+  {
+    std::lock_guard<std::mutex> lk(c->mu);
+    Slot* s = nullptr;
+    if (int rc = resolve_models_slot(c, epoch, &s)) return rc;
+    if (R == 0) return 0;
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaStreamWaitEvent(st, s->models_ready, 0));
+    uint32_t* d_ids = reinterpret_cast<uint32_t*>(c->d_out);     // R x 8 B staging holds R ids + R results
+    uint32_t* d_res = d_ids + R;
+    CUDA_TRY(cudaMemcpyAsync(d_ids, ids, (size_t)R * 4, cudaMemcpyHostToDevice, st));
+    lig_pick_models_stream_kernel<<<(R + kTile - 1) / kTile, kGroupThreads, 0, st>>>(
+        d_ids, d_res, R, reinterpret_cast<const uint4*>(s->d_cls), s->d_lists, s->A, s->d_mtab, s->n_models,
+        seed, first_index, reinterpret_cast<int4*>(c->d_reqs));
+    CUDA_TRY(cudaGetLastError());
+    c->launches++;
+    CUDA_TRY(cudaMemcpyAsync(reqs_out, c->d_reqs, (size_t)R * sizeof(lig_req), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(out, d_res, (size_t)R * 4, cudaMemcpyDeviceToHost, st));
+    if (int rc = note_reader(*s, st)) return rc;
+  }
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int lig_pick_kernel_info(lig_ctx* c, uint64_t epoch, char* name, int name_len, int* grid, int* threads,
+                         int* table_bytes, int* tables_in_smem) {
+  if (!c) return fail(LIG_ERR_INVALID, "lig_pick_kernel_info: ctx is null");
+  std::lock_guard<std::mutex> lk(c->mu);
+  Slot* s = nullptr;
+  if (int rc = resolve_slot(c, epoch, &s)) return rc;
+  CUDA_TRY(cudaSetDevice(c->device));
+  CUDA_TRY(cudaEventSynchronize(s->ready));
+  const bool tab = tables_fit_smem(c, *s, false);
+  const char* nm = "lig_pick_queue_kernel";
+  int g = 0, t = kPickThreads;
+  if (c->pick_kernel == 0) {
+    nm = "lig_pick_persistent_kernel";
+    g = c->persist_grid[0][tab ? 1 : 0];
+    t = persist_threads(c->tma_groups);
+  } else if (c->pick_kernel == 1) {
+    nm = "lig_pick_loop_kernel";
+    g = c->loop_grid[tab ? 1 : 0];
+    t = kLoopThreads;
+  }
+  if (name && name_len > 0) snprintf(name, (size_t)name_len, "%s", nm);
+  if (grid) *grid = g;
+  if (threads) *threads = t;
+  if (table_bytes) *table_bytes = (int)s->h_hdr->bytes;
+  if (tables_in_smem) *tables_in_smem = tab ? 1 : 0;
   return 0;
 }
 

@@ -1071,8 +1071,9 @@ struct QueueParams {
 };
 
 // Shared-memory budget of the compact tables (CompactHeader blob) inside the persistent kernels:
-// 64 KB hold C4's 2050 entries (32 KB) and its 5.5 K list entries (11 KB) with room to spare.
-constexpr uint32_t kTabBudget = 64 * 1024;
+// 72 KB hold C4's 2050 class entries (32 KB), its 5.5 K list entries (11 KB) and a ~1100-model
+// table (18 KB) of the model-request kernels.
+constexpr uint32_t kTabBudget = 72 * 1024;
 
 __host__ __device__ constexpr int persist_threads(int groups) { return groups * kGroupThreads + 32; }
 __host__ __device__ constexpr size_t persist_smem_bytes(int groups, int stages, bool bulk_store, bool tab_smem) {
@@ -1317,6 +1318,256 @@ lig_pick_loop_kernel(const __grid_constant__ QueueParams qp, const uint4* __rest
 #pragma unroll
     for (int j = 0; j < 4; ++j) cur[j] = nxt[j];
     g = g2; b = b2; t = t2; it = it2; n = n2;
+  }
+}
+
+// ---- K2e: model requests (the step before Schedule, fused into the pick) --------------------------
+// Replaces per request handlers/request.go:42-56: FetchModelData (backend/datastore.go:70-76),
+// RandomWeightedDraw (datastore.go:78-98), IsCritical (datastore.go:100-105).  A request is one
+// 32-bit model id, a result one 32-bit lig_mpick: 8 bytes per decision.
+//
+// Model blob (global; the persistent kernel appends it to the class tables in shared memory):
+//   [ header 16 B ][ entries: n_models x 16 B ][ targets: 8 B each ]
+//   entry.x  bits 0-7 n_targets | 8 critical | 9 present | 12-16 shift (Int31n magic of `total`)
+//   entry.y  magic (see ClassEntry) of total = sum of weights, when n_targets >= 2
+//   entry.z  total
+//   entry.w  n_targets >= 2: index of the first target record; == 1: that target's adapter id;
+//            == 0: the model's own adapter id (TargetModels empty, request.go:47)
+//   target   {adapter_id, inclusive cumulative weight}: the reference's loop "if randomVal <
+//            Weight return; randomVal -= Weight" (datastore.go:91-97) picks the first k with
+//            randomVal < cum[k] when the weights are non-negative.
+struct ModelHeader {
+  uint32_t bytes;        // header + entries + targets, multiple of 16
+  uint32_t n_models;
+  uint32_t n_target_records;
+  uint32_t reserved;
+};
+constexpr uint32_t kModelCritical = 1u << 8, kModelPresent = 1u << 9;
+
+struct ModelTables {         // where a kernel reads the model blob from (shared or global memory)
+  const uint4* entries;
+  const uint2* targets;
+  uint32_t n_models;
+};
+
+__device__ __forceinline__ uint32_t pack_mpick(int pod, uint32_t status, uint32_t target) {
+  return ((uint32_t)pod & 0xffffu) | (status << 16) | (target << 24);
+}
+
+// resolve: model id -> (adapter, critical, target index); false = LIG_NO_MODEL.
+template <bool kSmem>
+__device__ __forceinline__ bool resolve_model(uint32_t m, const ModelTables& mt, uint64_t seed, uint64_t key,
+                                              uint32_t* adapter, uint32_t* critical, uint32_t* target) {
+  *adapter = 0xffffffffu; *critical = 0; *target = 255u;
+  if (m >= mt.n_models) return false;
+  const uint4 e = kSmem ? mt.entries[m] : __ldg(mt.entries + m);
+  if (!(e.x & kModelPresent)) return false;
+  *critical = (e.x >> 8) & 1u;
+  const uint32_t nt = e.x & 0xffu;
+  if (nt <= 1u) {                      // no TargetModels, or a single one: nothing to draw
+    *adapter = e.w;
+    *target = nt ? 0u : 255u;
+    return true;
+  }
+  // randomVal = r.Int31n(weights)                                           datastore.go:90
+  const uint32_t total = e.z, shift = (e.x >> 12) & 31u;
+  const uint32_t q_limit = total > 1u ? 0x80000000u / total : 1u;
+  uint64_t state = seed ^ key ^ LIG_DRAW_DOMAIN;
+  uint32_t v = splitmix_int31(state);
+  uint32_t q = __umulhi(v, e.y) >> shift;
+  while (q >= q_limit) {
+    v = splitmix_int31(state);
+    q = __umulhi(v, e.y) >> shift;
+  }
+  const uint32_t r = total > 1u ? v - q * total : 0u;
+  uint32_t k = 0;
+  uint2 tr = kSmem ? mt.targets[e.w] : __ldg(mt.targets + e.w);
+  while (k + 1u < nt && r >= tr.y) {   // first k with randomVal < cum[k]       datastore.go:91-97
+    ++k;
+    tr = kSmem ? mt.targets[e.w + k] : __ldg(mt.targets + e.w + k);
+  }
+  *adapter = tr.x;
+  *target = k;
+  return true;
+}
+
+// One model request end to end; the class lookup as in pick_one / pick_one_smem.
+template <bool kSmem>
+__device__ __forceinline__ uint32_t pick_model(uint32_t m, uint64_t key, const ModelTables& mt,
+                                               const uint4* cls, const uint16_t* lists, uint32_t A,
+                                               uint64_t seed) {
+  uint32_t adapter, critical, target;
+  if (!resolve_model<kSmem>(m, mt, seed, key, &adapter, &critical, &target))
+    return pack_mpick(-1, (uint32_t)LIG_NO_MODEL, 255u);
+  const int4 r = make_int4((int)adapter, (int)critical, (int)(uint32_t)key, (int)(uint32_t)(key >> 32));
+  const int2 p = kSmem ? pick_one_smem(r, cls, lists, A, seed) : pick_one(r, cls, lists, A, seed);
+  return pack_mpick(p.x, (uint32_t)p.y & 3u, target);
+}
+
+struct MQueueItem {
+  const uint32_t* ids;
+  uint32_t* out;
+  uint64_t seed;
+  uint64_t first_index;
+};
+constexpr int kMaxInlineMItems = 64;
+struct MQueueParams {
+  int n_batches;
+  int R;
+  int tiles_per_batch;
+  int total_tiles;
+  const MQueueItem* dev_items;
+  MQueueItem items[kMaxInlineMItems];
+};
+
+__device__ __forceinline__ MQueueItem mqueue_item(const MQueueParams& qp, int b) {
+  if (qp.n_batches <= kMaxInlineMItems) return qp.items[b];
+  MQueueItem it;
+  const unsigned long long* p = reinterpret_cast<const unsigned long long*>(qp.dev_items + b);
+  it.ids = reinterpret_cast<const uint32_t*>(__ldg(p));
+  it.out = reinterpret_cast<uint32_t*>(__ldg(p + 1));
+  it.seed = __ldg(p + 2);
+  it.first_index = __ldg(p + 3);
+  return it;
+}
+
+__host__ __device__ constexpr size_t mpersist_smem_bytes(int stages, bool tab_smem) {
+  return (tab_smem ? (size_t)kTabBudget : 0) + (size_t)stages * kTile * 4 + 2u * (size_t)stages * 8 + 64;
+}
+
+// Persistent kernel for HBM-resident model-id batches: same structure as K2c (TMA ring, consumer
+// groups, tables in shared memory), 4 KB tiles, every thread takes 4 consecutive requests
+// (one LDS.128 in, one 16-byte store out).
+template <int kGroups, int kStages, bool kTabSmem>
+__global__ void __launch_bounds__(persist_threads(kGroups), 2 / kGroups > 0 ? 2 / kGroups : 1)
+lig_pick_models_kernel(const __grid_constant__ MQueueParams qp, const uint4* __restrict__ cls,
+                       const uint16_t* __restrict__ lists, int A,
+                       const unsigned char* __restrict__ ctab, uint32_t ctab_bytes,
+                       const unsigned char* __restrict__ mtab, uint32_t mtab_bytes, uint32_t n_models) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  unsigned char* base = smem + (kTabSmem ? kTabBudget : 0u);
+  uint4* in_ring = reinterpret_cast<uint4*>(base);                                  // [kStages][kTile / 4]
+  uint64_t* full = reinterpret_cast<uint64_t*>(base + (size_t)kStages * kTile * 4);
+  uint64_t* empty = full + kStages;
+  uint64_t* tab_bar = empty + kStages;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(empty + s, kGroupThreads / 32);
+    }
+    mbar_init(tab_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int tpb = qp.tiles_per_batch, total = qp.total_tiles, R = qp.R;
+
+  if (warp == kGroups * (kGroupThreads / 32)) {
+    if (lane == 0) {
+      if (kTabSmem) {      // class tables, then the model table right behind them
+        mbar_arrive_expect_tx(tab_bar, ctab_bytes + mtab_bytes);
+        bulk_load(smem, ctab, ctab_bytes, tab_bar);
+        bulk_load(smem + ctab_bytes, mtab, mtab_bytes, tab_bar);
+      }
+      const int step = (int)gridDim.x;
+      int b = (int)blockIdx.x / tpb;
+      int t = (int)blockIdx.x - b * tpb;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int g = (int)blockIdx.x; g < total; g += step) {
+        mbar_wait(empty + stage, phase ^ 1u);
+        const MQueueItem it = mqueue_item(qp, b);
+        const uint32_t n = (uint32_t)min(kTile, R - t * kTile);
+        const uint32_t bytes = (n * 4u + 15u) & ~15u;   // the buffers are padded to 16 bytes by the ABI
+        mbar_arrive_expect_tx(full + stage, bytes);
+        bulk_load(in_ring + (size_t)stage * (kTile / 4), it.ids + (size_t)t * kTile, bytes, full + stage);
+        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        t += step;
+        while (t >= tpb) { t -= tpb; ++b; }
+      }
+    }
+    return;
+  }
+
+  const int grp = warp / (kGroupThreads / 32);
+  const int tid = (int)threadIdx.x - grp * kGroupThreads;
+  const int step = (int)gridDim.x * kGroups;
+  int g = (int)blockIdx.x + grp * (int)gridDim.x;
+  int b = g / tpb;
+  int t = g - b * tpb;
+  int stage = grp % kStages;
+  uint32_t phase = (uint32_t)(grp / kStages) & 1u;
+  ModelTables mt;
+  const uint4* tab = cls;
+  const uint16_t* pool = lists;
+  if (kTabSmem) {
+    tab = reinterpret_cast<const uint4*>(smem + sizeof(CompactHeader));
+    pool = reinterpret_cast<const uint16_t*>(smem + sizeof(CompactHeader) + (size_t)2 * ((size_t)A + 1) * sizeof(ClassEntry));
+    mt.entries = reinterpret_cast<const uint4*>(smem + ctab_bytes + sizeof(ModelHeader));
+  } else {
+    mt.entries = reinterpret_cast<const uint4*>(mtab + sizeof(ModelHeader));
+  }
+  mt.targets = reinterpret_cast<const uint2*>(mt.entries + n_models);
+  mt.n_models = n_models;
+  if (kTabSmem) mbar_wait(tab_bar, 0);
+  for (; g < total; g += step) {
+    const MQueueItem it = mqueue_item(qp, b);
+    const int n = min(kTile, R - t * kTile);
+    mbar_wait(full + stage, phase);
+    const uint4 ids = in_ring[(size_t)stage * (kTile / 4) + tid];
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty + stage);
+    stage += kGroups;
+    while (stage >= kStages) { stage -= kStages; phase ^= 1u; }
+    const int i0 = tid * 4;
+    const uint64_t key0 = it.first_index + (uint64_t)t * kTile + (uint64_t)i0;
+    uint4 o;
+    o.x = pick_model<kTabSmem>(ids.x, key0 + 0, mt, tab, pool, (uint32_t)A, it.seed);
+    o.y = pick_model<kTabSmem>(ids.y, key0 + 1, mt, tab, pool, (uint32_t)A, it.seed);
+    o.z = pick_model<kTabSmem>(ids.z, key0 + 2, mt, tab, pool, (uint32_t)A, it.seed);
+    o.w = pick_model<kTabSmem>(ids.w, key0 + 3, mt, tab, pool, (uint32_t)A, it.seed);
+    uint32_t* dst = it.out + (size_t)t * kTile + i0;
+    if (i0 + 4 <= n) {
+      asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1, %2, %3, %4};"
+                   :: "l"(dst), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+    } else {
+      if (i0 + 0 < n) dst[0] = o.x;
+      if (i0 + 1 < n) dst[1] = o.y;
+      if (i0 + 2 < n) dst[2] = o.z;
+    }
+    t += step;
+    while (t >= tpb) { t -= tpb; ++b; }
+  }
+}
+
+// The plain form: one short-lived CTA per 1024 requests, LDG/STG only.  Host-buffer path (`ids` /
+// `out` may be page-locked host memory), unaligned device buffers, and the resolve-only test hook
+// (reqs_out != nullptr: also write the 16-byte descriptor built for every request).
+__global__ void __launch_bounds__(kGroupThreads)
+lig_pick_models_stream_kernel(const uint32_t* __restrict__ ids, uint32_t* __restrict__ out, int R,
+                              const uint4* __restrict__ cls, const uint16_t* __restrict__ lists, int A,
+                              const unsigned char* __restrict__ mtab, uint32_t n_models, uint64_t seed,
+                              uint64_t first_index, int4* __restrict__ reqs_out) {
+  ModelTables mt;
+  mt.entries = reinterpret_cast<const uint4*>(mtab + sizeof(ModelHeader));
+  mt.targets = reinterpret_cast<const uint2*>(mt.entries + n_models);
+  mt.n_models = n_models;
+  const int first = (int)blockIdx.x * kTile + (int)threadIdx.x;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int i = first + j * kGroupThreads;
+    if (i >= R) break;
+    const uint32_t m = __ldg(ids + i);
+    const uint64_t key = first_index + (uint64_t)i;
+    if (reqs_out) {
+      uint32_t adapter, critical, target;
+      const bool ok = resolve_model<false>(m, mt, seed, key, &adapter, &critical, &target);
+      reqs_out[i] = make_int4((int)adapter, (int)critical, (int)(uint32_t)key, (int)(uint32_t)(key >> 32));
+      out[i] = pack_mpick(-1, ok ? (uint32_t)LIG_OK : (uint32_t)LIG_NO_MODEL, target);
+    } else {
+      out[i] = pick_model<false>(m, key, mt, cls, lists, (uint32_t)A, seed);
+    }
   }
 }
 

@@ -7,7 +7,7 @@ from typing import Optional, Tuple
 import numpy as np
 
 from . import _native as N
-from .packer import PICK_DTYPE, REQ_DTYPE, PackedSnapshot, _ptr
+from .packer import MPICK_DTYPE, PICK_DTYPE, REQ_DTYPE, PackedModels, PackedSnapshot, _ptr
 
 
 class Engine:
@@ -77,6 +77,50 @@ class Engine:
 
     def schedule_wait(self, ticket: int) -> None:
         N.check(self._lib.lig_schedule_wait(self._ctx, ticket))
+
+    # ---- model requests: the resolve step of HandleRequestBody on the device ----
+    def upload_models(self, epoch: int, models: PackedModels) -> None:
+        N.check(self._lib.lig_upload_models(self._ctx, epoch, models.n_models, _ptr(models.target_offsets),
+                                            _ptr(models.target_adapter_ids), _ptr(models.target_weights),
+                                            _ptr(models.critical), _ptr(models.self_adapter_ids),
+                                            _ptr(models.present)))
+
+    def schedule_models_batch(self, epoch: int, seed: int, model_ids: np.ndarray, first_index: int = 0,
+                              out: Optional[np.ndarray] = None) -> np.ndarray:
+        assert model_ids.dtype == np.uint32 and model_ids.flags.c_contiguous
+        R = int(model_ids.shape[0])
+        if out is None:
+            out = np.empty(R, dtype=MPICK_DTYPE)
+        N.check(self._lib.lig_schedule_models_batch(self._ctx, epoch, seed, first_index, _ptr(model_ids), R, _ptr(out)))
+        return out
+
+    def schedule_models_batch_ptr(self, epoch: int, seed: int, first_index: int, h_ids: int, R: int, h_out: int) -> None:
+        N.check(self._lib.lig_schedule_models_batch(self._ctx, epoch, seed, first_index, h_ids, R, h_out))
+
+    def schedule_models_batches_device(self, epoch: int, seed: int, first_index: int, d_ids_ptrs, R: int,
+                                       d_out_ptrs, stream: int = 0) -> None:
+        n = len(d_ids_ptrs)
+        a = (C.c_void_p * n)(*d_ids_ptrs)
+        b = (C.c_void_p * n)(*d_out_ptrs)
+        N.check(self._lib.lig_schedule_models_batches_device(self._ctx, epoch, seed, first_index, a, R, b, n,
+                                                             stream or None))
+
+    def resolve_models(self, epoch: int, seed: int, model_ids: np.ndarray, first_index: int = 0):
+        assert model_ids.dtype == np.uint32 and model_ids.flags.c_contiguous
+        R = int(model_ids.shape[0])
+        reqs = np.empty(R, dtype=REQ_DTYPE)
+        out = np.empty(R, dtype=MPICK_DTYPE)
+        N.check(self._lib.lig_resolve_models(self._ctx, epoch, seed, first_index, _ptr(model_ids), R,
+                                             _ptr(reqs), _ptr(out)))
+        return reqs, out
+
+    def pick_kernel_info(self, epoch: int) -> dict:
+        name = C.create_string_buffer(64)
+        grid, threads, tb, in_smem = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        N.check(self._lib.lig_pick_kernel_info(self._ctx, epoch, name, 64, C.byref(grid), C.byref(threads),
+                                               C.byref(tb), C.byref(in_smem)))
+        return {"kernel": name.value.decode(), "grid": grid.value, "threads": threads.value,
+                "table_bytes": tb.value, "tables_in_smem": bool(in_smem.value)}
 
     # ---- one process per GPU: NCCL inside the library ----
     def comm_unique_id(self) -> bytes:

@@ -12,8 +12,8 @@ from typing import List
 
 import numpy as np
 
-from .packer import REQ_DTYPE, PackedSnapshot, pack_columns
-from .backend import Pod
+from .packer import REQ_DTYPE, PackedModels, PackedSnapshot, pack_columns, pack_models
+from .backend import CRITICAL, DEFAULT, SHEDDABLE, InferenceModel, InferenceModelSpec, Pod, TargetModel
 
 SNAPSHOT_SEED = 0xC0FFEE
 REQUEST_SEED = 0xBADC0DE
@@ -110,3 +110,64 @@ def make_requests(R: int, A: int, seed: int = REQUEST_SEED, out: np.ndarray = No
 def algorithmic_bytes(R: int, P: int, A: int) -> int:
     """24 R + 16 P + 4 A ceil(P/32)  (SURVEY.md section 8d)."""
     return 24 * R + 16 * P + 4 * A * ((P + 31) // 32)
+
+
+# ---- synthetic InferenceModels (the datastore the request pre-step reads) ------------------------
+# The three weight tables of the reference's own test (backend/datastore_test.go:9-76).
+WEIGHT_TABLES = ([("canary", 50), ("v1", 50)], [("canary", 25), ("v1.1", 55), ("v1", 50)],
+                 [("canary", 20), ("v1.1", 20), ("v1", 10)])
+N_SPLIT_MODELS = 64
+
+
+def _mix(x: int) -> int:
+    x = (x + 0x9E3779B97F4A7C15) & ((1 << 64) - 1)
+    x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & ((1 << 64) - 1)
+    x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & ((1 << 64) - 1)
+    return x ^ (x >> 31)
+
+
+def make_models(A: int) -> List[InferenceModel]:
+    """A + 1 + N_SPLIT_MODELS InferenceModels over the A adapters of a synthetic snapshot:
+      model-<a>   one target model adapter-<a> (weight 100); Critical for ~half of them
+      base-model  no TargetModels: the requested model name passes through (request.go:47)
+      split-<j>   2-3 weighted target models with the weight tables of datastore_test.go:9-76,
+                  the targets being adapters (or, for one in eight, a never-loaded adapter name)"""
+    models = []
+    for a in range(A):
+        crit = CRITICAL if _mix(a) & 1 else (DEFAULT if _mix(a) & 2 else SHEDDABLE)
+        models.append(InferenceModel(f"model-{a}", InferenceModelSpec(
+            ModelName=f"model-{a}", Criticality=crit, TargetModels=[TargetModel(adapter_name(a), 100)])))
+    models.append(InferenceModel(UNKNOWN_MODEL, InferenceModelSpec(ModelName=UNKNOWN_MODEL, Criticality=None)))
+    for j in range(N_SPLIT_MODELS):
+        table = WEIGHT_TABLES[j % 3]
+        tms = []
+        for k, (_, w) in enumerate(table):
+            t = _mix(1000 * j + k) % max(A, 1)
+            name = adapter_name(t) if (A and (_mix(7 * j + k) % 8)) else f"unloaded-{j}-{k}"
+            tms.append(TargetModel(name, w))
+        models.append(InferenceModel(f"split-{j}", InferenceModelSpec(
+            ModelName=f"split-{j}", Criticality=CRITICAL if j & 1 else DEFAULT, TargetModels=tms)))
+    return models
+
+
+def make_model_requests(R: int, A: int, seed: int = REQUEST_SEED) -> np.ndarray:
+    """uint32 model ids: 89 % model-<a> with a ~ Zipf(1.1), 3 % base-model, 8 % split-<j> (uniform),
+    0.05 % ids no InferenceModel exists for (FetchModelData returns nil)."""
+    rng = np.random.default_rng(seed)
+    n_models = A + 1 + N_SPLIT_MODELS
+    if A > 0:
+        cdf = np.cumsum(_zipf_weights(A))
+        ids = np.minimum(np.searchsorted(cdf, rng.random(R), side="right"), A - 1).astype(np.uint32)
+    else:
+        ids = np.full(R, A, dtype=np.uint32)
+    u = rng.random(R)
+    ids[u < 0.03] = A
+    split = (u >= 0.03) & (u < 0.11)
+    ids[split] = (A + 1 + rng.integers(0, N_SPLIT_MODELS, int(split.sum()))).astype(np.uint32)
+    ids[u > 0.9995] = n_models + 5
+    return np.ascontiguousarray(ids, dtype=np.uint32)
+
+
+def oracle_model_records(models: List[InferenceModel]) -> List[dict]:
+    return [dict(name=m.Spec.ModelName, critical=(m.Spec.Criticality == CRITICAL),
+                 targets=[(t.Name, t.Weight) for t in m.Spec.TargetModels]) for m in models]

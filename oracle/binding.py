@@ -18,6 +18,9 @@ LIB_PATH = os.path.join(_HERE, "liblig_oracle.so")
 LIGO_OK, LIGO_DROP, LIGO_EMPTY, LIGO_ERROR = 0, 1, 2, 3
 REQ_DTYPE = np.dtype([("adapter_id", "<i4"), ("flags", "<u4"), ("rand_key", "<u8")])
 PICK_DTYPE = np.dtype([("pod_idx", "<i4"), ("status", "<u2"), ("n_survivors", "<u2")])
+MPICK_DTYPE = np.dtype([("pod_idx", "<i2"), ("status", "u1"), ("target_idx", "u1")])
+LIGO_NO_MODEL, LIGO_NO_TARGET = 3, 4
+LIGO_DRAW_DOMAIN = 0xA0761D6478BD642F
 
 FILTER_FUNCS = {
     "leastQueuingFilterFunc": 0, "leastKVCacheFilterFunc": 1, "lowLoRACostPredicate": 2,
@@ -57,6 +60,21 @@ def load() -> C.CDLL:
     lib.lig_oracle_schedule_batch.argtypes = [vp, cpp, i32, C.c_char_p, vp, i32, u64, vp, vp, i32]
     lib.lig_oracle_soa_schedule_batch.argtypes = [i32, i32, vp, vp, vp, vp, vp, dbl, i64, i64, vp, i32, u64,
                                                   vp, vp, i32]
+    lib.lig_oracle_classtab_build.argtypes = [i32, i32, vp, vp, vp, vp, vp, dbl, i64, i64, i32]
+    lib.lig_oracle_classtab_build.restype = vp
+    lib.lig_oracle_classtab_free.argtypes = [vp]
+    lib.lig_oracle_classtab_free.restype = None
+    lib.lig_oracle_classtab_schedule_batch.argtypes = [vp, vp, i32, u64, vp, i32]
+    lib.lig_oracle_classtab_class.argtypes = [vp, i32, i32, C.POINTER(i32), C.POINTER(i32), vp]
+    lib.lig_oracle_models_new.argtypes = [i32]
+    lib.lig_oracle_models_new.restype = vp
+    lib.lig_oracle_models_free.argtypes = [vp]
+    lib.lig_oracle_models_free.restype = None
+    lib.lig_oracle_models_set.argtypes = [vp, i32, C.c_char_p, i32, cpp, vp, i32]
+    lib.lig_oracle_weighted_select.argtypes = [vp, i32, C.c_int32]
+    lib.lig_oracle_random_weighted_draw.argtypes = [vp, i32, u64]
+    lib.lig_oracle_resolve.argtypes = [vp, i32, u64, u64, C.POINTER(C.c_char_p), C.POINTER(i32), C.POINTER(i32)]
+    lib.lig_oracle_schedule_models_batch.argtypes = [vp, vp, vp, i32, u64, u64, vp]
     lib.lig_oracle_splitmix64_next.argtypes = [C.POINTER(u64)]
     lib.lig_oracle_splitmix64_next.restype = u64
     lib.lig_oracle_int31n.argtypes = [C.POINTER(u64), C.c_int32]
@@ -174,3 +192,90 @@ def splitmix64_stream(state: int, n: int) -> List[int]:
 def int31n(state: int, n: int) -> int:
     st = C.c_uint64(state)
     return int(load().lig_oracle_int31n(C.byref(st), n))
+
+
+class ClassTable:
+    """The class-table CPU arm (lig_oracle_classtab.c): tree walked once per (critical, adapter)
+    class per snapshot, then table lookup + Int31n per request."""
+
+    def __init__(self, P, A, kv, q, n_active, max_active, bitmap, thresholds=(0.8, 5, 50), nthreads=1):
+        self._lib = load()
+        self._keep = [np.ascontiguousarray(kv, dtype=np.float64), np.ascontiguousarray(q, dtype=np.int32),
+                      np.ascontiguousarray(n_active, dtype=np.uint16), np.ascontiguousarray(max_active, dtype=np.uint16),
+                      np.ascontiguousarray(bitmap, dtype=np.uint32)]
+        ptr = lambda a: a.ctypes.data if a.size else None
+        self.P, self.A = P, A
+        self._t = self._lib.lig_oracle_classtab_build(P, A, *[ptr(a) for a in self._keep], thresholds[0],
+                                                      thresholds[1], thresholds[2], nthreads)
+        assert self._t
+
+    def __del__(self):
+        try:
+            if self._t:
+                self._lib.lig_oracle_classtab_free(self._t)
+                self._t = None
+        except Exception:
+            pass
+
+    def schedule_batch(self, reqs: np.ndarray, seed: int, nthreads: int = 1, out: Optional[np.ndarray] = None):
+        assert reqs.dtype == REQ_DTYPE and reqs.flags.c_contiguous
+        R = int(reqs.shape[0])
+        if out is None:
+            out = np.zeros(R, dtype=PICK_DTYPE)
+        rc = self._lib.lig_oracle_classtab_schedule_batch(self._t, reqs.ctypes.data if R else None, R, seed,
+                                                          out.ctypes.data if R else None, nthreads)
+        assert rc == 0
+        return out
+
+    def klass(self, critical: bool, adapter_id: int):
+        st, n = C.c_int(), C.c_int()
+        lst = np.zeros(max(self.P, 1), dtype=np.uint16)
+        assert self._lib.lig_oracle_classtab_class(self._t, int(critical), adapter_id, C.byref(st), C.byref(n),
+                                                   lst.ctypes.data) == 0
+        return st.value, n.value, lst[: n.value].tolist()
+
+
+class Models:
+    """The datastore's InferenceModels by dense id (lig_oracle_models.c)."""
+
+    def __init__(self, models: Sequence[dict]):
+        """models: dicts with name, critical, targets=[(name, weight), ...]; None = absent id."""
+        self._lib = load()
+        self.n = len(models)
+        self._m = self._lib.lig_oracle_models_new(self.n)
+        for i, m in enumerate(models):
+            if m is None:
+                continue
+            tn = [t[0] for t in m.get("targets", [])]
+            tw = np.array([t[1] for t in m.get("targets", [])], dtype=np.int32)
+            rc = self._lib.lig_oracle_models_set(self._m, i, m["name"].encode(), int(bool(m.get("critical"))),
+                                                 _names(tn), tw.ctypes.data if tw.size else None, len(tn))
+            assert rc == 0
+
+    def __del__(self):
+        try:
+            if self._m:
+                self._lib.lig_oracle_models_free(self._m)
+                self._m = None
+        except Exception:
+            pass
+
+    def weighted_select(self, model: int, random_val: int) -> int:
+        return int(self._lib.lig_oracle_weighted_select(self._m, model, random_val))
+
+    def random_weighted_draw(self, model: int, state: int) -> int:
+        return int(self._lib.lig_oracle_random_weighted_draw(self._m, model, state))
+
+    def resolve(self, model: int, seed: int, rand_key: int):
+        name, crit, tgt = C.c_char_p(), C.c_int(), C.c_int()
+        rc = self._lib.lig_oracle_resolve(self._m, model, seed, rand_key, C.byref(name), C.byref(crit), C.byref(tgt))
+        return rc, (name.value.decode() if rc == 0 else None), bool(crit.value), tgt.value
+
+    def schedule_batch(self, pool: "Pool", model_ids: np.ndarray, seed: int, first_index: int = 0) -> np.ndarray:
+        assert model_ids.dtype == np.uint32 and model_ids.flags.c_contiguous
+        R = int(model_ids.shape[0])
+        out = np.zeros(R, dtype=MPICK_DTYPE)
+        rc = self._lib.lig_oracle_schedule_models_batch(pool._p, self._m, model_ids.ctypes.data if R else None, R,
+                                                        seed, first_index, out.ctypes.data if R else None)
+        assert rc == 0
+        return out

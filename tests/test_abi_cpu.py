@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from llm_instance_gateway_b200 import _native as N
-from llm_instance_gateway_b200.packer import PICK_DTYPE, REQ_DTYPE, pack_columns, pack_pod_metrics
+from llm_instance_gateway_b200.packer import PICK_DTYPE, REQ_DTYPE, RangeError, pack_columns, pack_pod_metrics
 from llm_instance_gateway_b200.backend import Metrics, Pod, PodMetrics
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -63,19 +63,65 @@ def test_snapshot_bytes_and_layout():
     assert np.array_equal(bm, np.array([[0xFFFFFFFF, 1], [0xFFFFFFFF, 1]], dtype=np.uint32))
 
 
+def c_pack(lib, kv, q64, na64, ma64, bitmap):
+    """The C helpers (lig_pack_pods + lig_pack_snapshot), the way a non-Python host uses them."""
+    P = len(kv)
+    kv = np.ascontiguousarray(kv, dtype=np.float64)
+    q64, na64, ma64 = (np.ascontiguousarray(a, dtype=np.int64) for a in (q64, na64, ma64))
+    q, na, ma = np.zeros(P, np.int32), np.zeros(P, np.uint16), np.zeros(P, np.uint16)
+    p = lambda a: a.ctypes.data if a.size else None
+    rc = lib.lig_pack_pods(P, p(q64), p(na64), p(ma64), p(q), p(na), p(ma))
+    if rc != 0:
+        return rc, None
+    bitmap = np.ascontiguousarray(bitmap, dtype=np.uint32)
+    A = bitmap.shape[0]
+    out = np.zeros(lib.lig_snapshot_bytes(P, A), dtype=np.uint8)
+    N.check(lib.lig_pack_snapshot(out.ctypes.data, P, A, p(kv), p(q), p(na), p(ma), p(bitmap)))
+    return 0, out
+
+
 def test_pack_pods_range_checks_and_saturation():
+    """The numpy packer and the C helpers narrow identically: same bytes, same refusals."""
     lib = N.load()
-    ok = pack_columns([0.1, 0.2, 0.3], [2**31 - 1, -(2**31), 0], [0, 1, 65534], [-7, 70000, 2**40],
-                      np.zeros((0, 1), dtype=np.uint32))
+    empty = np.zeros((0, 1), dtype=np.uint32)
+    ok = pack_columns([0.1, 0.2, 0.3], [2**31 - 1, -(2**31), 0], [0, 1, 65534], [-7, 70000, 2**40], empty)
     assert ok.q.tolist() == [2**31 - 1, -(2**31), 0]
     assert ok.max_active.tolist() == [0, 65535, 65535]      # saturated, predicate-preserving
+    rc, blob = c_pack(lib, [0.1, 0.2, 0.3], [2**31 - 1, -(2**31), 0], [0, 1, 65534], [-7, 70000, 2**40], empty)
+    assert rc == 0 and np.array_equal(blob, ok.blob())
     for bad_q in (2**31, -(2**31) - 1):
-        with pytest.raises(N.LigError) as ei:
-            pack_columns([0.0], [bad_q], [0], [0], np.zeros((0, 1), dtype=np.uint32))
-        assert ei.value.code == N.LIG_ERR_RANGE and "int32" in str(ei.value)
-    with pytest.raises(N.LigError):
-        pack_columns([0.0], [0], [65535], [0], np.zeros((0, 1), dtype=np.uint32))
+        with pytest.raises(RangeError) as ei:
+            pack_columns([0.0], [bad_q], [0], [0], empty)
+        assert "int32" in str(ei.value)
+        assert c_pack(lib, [0.0], [bad_q], [0], [0], empty)[0] == N.LIG_ERR_RANGE
+        assert b"int32" in lib.lig_last_error()
+    with pytest.raises(RangeError):
+        pack_columns([0.0], [0], [65535], [0], empty)
+    assert c_pack(lib, [0.0], [0], [65535], [0], empty)[0] == N.LIG_ERR_RANGE
     assert lib.lig_pack_pods(1, None, None, None, None, None, None) == N.LIG_ERR_INVALID
+    # random pools, ragged P: identical blobs
+    rng = np.random.default_rng(3)
+    for P, A in [(1, 0), (31, 3), (32, 1), (33, 5), (100, 17), (257, 40)]:
+        W = (P + 31) // 32
+        kv = rng.random(P)
+        q = rng.integers(-5, 300, P)
+        na = rng.integers(0, 20, P)
+        ma = rng.integers(-3, 70000, P)
+        bm = rng.integers(0, 1 << 32, (A, W), dtype=np.uint64).astype(np.uint32)
+        rc, blob = c_pack(lib, kv, q, na, ma, bm)
+        assert rc == 0 and np.array_equal(blob, pack_columns(kv, q, na, ma, bm).blob()), (P, A)
+
+
+def test_the_workload_generator_does_not_load_the_cuda_library():
+    """bench.py --impl reference builds its inputs with workload.py / packer.py: pure numpy."""
+    import subprocess
+    import sys
+    code = ("import sys; from llm_instance_gateway_b200 import workload as WL; "
+            "s = WL.make_snapshot(64, 8); r = WL.make_requests(100, 8); s.packed.blob(); "
+            "import ctypes; "
+            "assert not any('liblig.so' in l for l in open('/proc/self/maps')), 'liblig.so was loaded'; "
+            "assert 'llm_instance_gateway_b200._native' not in sys.modules")
+    subprocess.check_call([sys.executable, "-c", code], cwd=ROOT)
 
 
 def test_pack_pod_metrics_interning_and_bitmap():
