@@ -4,8 +4,10 @@
 A "step" is one pass of the hot path over one batch of R synthetic request descriptors against a
 resident P-pod / A-adapter snapshot.  Default workload at N=1: BASELINE.json configs[3] run on one
 GPU (R = 2^20, P = 4096, A = 1024) — the configuration the 1/2/4/8-GPU metric is quoted on; it
-fits one GPU.  With N GPUs every rank schedules its own R-request shard of the same step against
-the NCCL-broadcast snapshot (weak scaling, no data-path collective).
+fits one GPU.  With N GPUs (one process per GPU) every rank schedules its own R-request shard of
+the same step (weak scaling, no data-path collective); the snapshot is replicated by ONE in-library
+ncclBroadcast per refresh tick (lig_comm_upload_snapshot_device).  The `strong` object of the line
+is the same measurement with ONE R-request batch sharded over the N GPUs (north_star's C4).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
                     [--workload C4|C3|C2|C5] [--requests-per-gpu R]
@@ -28,7 +30,7 @@ if ROOT not in sys.path:
 
 import numpy as np  # noqa: E402
 
-from llm_instance_gateway_b200 import workload as WL  # noqa: E402
+from llm_instance_gateway_b200 import workload as WL  # noqa: E402  (pure numpy: no CUDA library)
 
 METRIC = "routing decisions/sec (RxP batch)"
 UNIT = "decisions/s"
@@ -42,11 +44,17 @@ def workload_label(name, R, P, A):
             f"(BASELINE.json configs[{idx}])")
 
 
+def base_config(args, R, P, A, world):
+    """The part of `config` both arms print identically."""
+    return {"workload": workload_label(args.workload, R, P, A), "requests_per_gpu": R, "pods": P,
+            "adapters": A, "parallelism": f"request-sharded x{world}"}
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C4", choices=["C2", "C3", "C4", "C5"])
     ap.add_argument("--requests-per-gpu", type=int, default=0,
@@ -64,7 +72,10 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-streaming", action="store_true",
                     help="skip the C5 streaming leg (100K req/s Poisson, p50/p99 decision latency)")
-    ap.add_argument("--cpu-seconds", type=float, default=10.0, help="target CPU time of the baseline sample")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip k_sweep / strong / uniform-adapter / model-request legs")
+    ap.add_argument("--cpu-seconds", type=float, default=6.0, help="target CPU time of each baseline sample")
+    ap.add_argument("--stream-seconds", type=float, default=10.0)
     return ap.parse_args()
 
 
@@ -77,20 +88,26 @@ def hbm_peak():
         return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
-def committed_traffic(workload, steps_per_launch):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full captures
-    (profiles/traffic.json): per-step traffic of the merged queue kernel x steps per launch, or
-    the per-launch figure of the one-batch-per-launch kernel."""
+def committed_traffic(workload, info, steps_per_launch):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
+    (profiles/traffic.json), accepted only when that capture is of the kernel, grid and block size
+    this run launches; otherwise (None, why)."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
             t = json.load(fh).get(workload)
-        if not t:
-            return None
-        if steps_per_launch > 1:
-            return int(t["queue_kernel_bytes_per_step"] * steps_per_launch)
-        return int(t["stream_kernel_bytes_per_launch"])
-    except Exception:
-        return None
+    except Exception as ex:   # noqa: BLE001
+        return None, f"profiles/traffic.json unreadable: {ex}"
+    if not t:
+        return None, "no capture for this workload in profiles/traffic.json"
+    cap = t.get("capture", {})
+    for key in ("kernel", "grid", "threads"):
+        if cap.get(key) != info.get(key):
+            return None, (f"committed capture is of {cap.get('kernel')} grid={cap.get('grid')} threads={cap.get('threads')}, "
+                          f"this run launches {info.get('kernel')} grid={info.get('grid')} threads={info.get('threads')}")
+    if cap.get("steps_per_launch") != steps_per_launch:
+        return int(t["bytes_per_step"] * steps_per_launch), (
+            f"capture has {cap.get('steps_per_launch')} steps per launch; scaled per step")
+    return int(t["bytes_per_launch"]), "matches the launched kernel"
 
 
 class ClockSampler:
@@ -148,33 +165,70 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------
-def cpu_quota():
-    """cgroup CPU quota of this container in cores (None = unlimited), to read `cores` honestly."""
-    try:
-        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
-        return None if quota == "max" else float(quota) / float(period)
-    except Exception:
-        return None
-
-
-def cpu_reference_rate(snap, reqs, seed, nthreads, seconds):
-    """Time the oracle port (the reference's algorithm and data structures, in C) on a bounded
-    sample of the workload.  Returns (decisions/s, sample size)."""
-    from oracle import binding as oracle
-    pool = oracle.Pool(snap.pod_records())
-    names = snap.adapter_names()
-    probe = min(len(reqs), max(256, 64 * nthreads))
+def timed_rate(fn, n_probe, n_max, seconds):
+    """Run fn(n) on a probe, size the sample for ~`seconds`, time it.  Returns (rate, sample)."""
+    probe = max(1, min(n_probe, n_max))
     t0 = time.perf_counter()
-    pool.schedule_batch(names, WL.UNKNOWN_MODEL, np.ascontiguousarray(reqs[:probe]), seed, False, nthreads)
+    fn(probe)
     dt = max(time.perf_counter() - t0, 1e-6)
-    sample = int(min(len(reqs), max(probe, probe / dt * seconds)))
+    sample = int(min(n_max, max(probe, probe / dt * seconds)))
     t0 = time.perf_counter()
-    pool.schedule_batch(names, WL.UNKNOWN_MODEL, np.ascontiguousarray(reqs[:sample]), seed, False, nthreads)
-    dt = time.perf_counter() - t0
-    return sample / dt, sample
+    fn(sample)
+    return sample / (time.perf_counter() - t0), sample
 
 
-def streaming_leg(device, rate=1e5, seconds=3.0, threads=32, window_us=2):
+def cpu_arms(snap, models, reqs, model_ids, seed, seconds):
+    """Every CPU arm on the same inputs, with min(hardware threads, cgroup quota) threads:
+      port            the reference's algorithm AND data structures (C restatement of the Go code),
+                      including the resolve step (FetchModelData + RandomWeightedDraw + IsCritical)
+      optimised_cpu   same per-request tree walk on columns + bitmaps (no allocation, no strings)
+      class_table_cpu the GPU path's algorithmic restructuring on the host: the tree walked once
+                      per (critical, adapter) class per snapshot, a request = lookup + Int31n
+    """
+    from oracle import binding as oracle
+    nthr = oracle.usable_threads()
+    pool = oracle.Pool(snap.pod_records())
+    mo = oracle.Models(WL.model_records(models))
+    names = snap.adapter_names()
+    pk = snap.packed
+    v_port, s_port = timed_rate(lambda n: mo.schedule_batch(pool, np.ascontiguousarray(model_ids[:n]), seed, 0, nthr),
+                                64 * nthr, len(model_ids), seconds)
+    v_port1, s_port1 = timed_rate(lambda n: mo.schedule_batch(pool, np.ascontiguousarray(model_ids[:n]), seed, 0, 1),
+                                  64, len(model_ids), min(seconds, 2.0))
+    v_sched, s_sched = timed_rate(lambda n: pool.schedule_batch(names, WL.UNKNOWN_MODEL, np.ascontiguousarray(reqs[:n]),
+                                                                seed, False, nthr), 64 * nthr, len(reqs), min(seconds, 3.0))
+    v_soa, s_soa = timed_rate(lambda n: oracle.soa_schedule_batch(pk.P, pk.A, pk.kv, pk.q, pk.n_active, pk.max_active,
+                                                                  pk.bitmap, np.ascontiguousarray(reqs[:n]), seed,
+                                                                  False, nthr), 4096 * nthr, len(reqs), min(seconds, 3.0))
+    t0 = time.perf_counter()
+    tab = oracle.ClassTable(pk.P, pk.A, pk.kv, pk.q, pk.n_active, pk.max_active, pk.bitmap, nthreads=nthr)
+    build_s = time.perf_counter() - t0
+    out = np.zeros(len(reqs), dtype=oracle.PICK_DTYPE)
+    tab.schedule_batch(reqs, seed, nthr, out)                      # warm
+    reps = 0
+    t0 = time.perf_counter()
+    while time.perf_counter() - t0 < min(seconds, 2.0):
+        tab.schedule_batch(reqs, seed + reps, nthr, out)
+        reps += 1
+    v_tab = len(reqs) * reps / (time.perf_counter() - t0)
+    return {
+        "value": v_port, "unit": UNIT, "cores": nthr, "kind": "port",
+        "sample": f"first {s_port} model requests of batch 0 of the same workload (resolve + Schedule per request)",
+        "hardware_threads": oracle.hardware_threads(), "cgroup_cpu_quota_cores": oracle.cpu_quota_cores(),
+        "single_thread": {"value": v_port1, "sample": s_port1},
+        "schedule_only": {"value": v_sched, "sample": s_sched,
+                          "note": "Scheduler.Schedule on pre-resolved requests (no model lookup / target draw)"},
+        "optimised_cpu": {"value": v_soa, "cores": nthr, "sample": s_soa,
+                          "note": "oracle/lig_oracle_soa.c: same per-request tree walk on columns + adapter bitmaps"},
+        "class_table_cpu": {"value": v_tab, "cores": nthr, "sample": len(reqs) * reps,
+                            "table_build_ms": build_s * 1e3,
+                            "note": "oracle/lig_oracle_classtab.c: the GPU path's restructuring on the host — 2(A+1) "
+                                    "tree walks per snapshot, then lookup + Int31n per request, host-resident buffers"},
+        "note": "C restatement of the Go scheduler with the reference's data structures (Go toolchain absent "
+                "from the image); every arm runs min(hardware threads, cgroup quota) threads"}
+
+
+def streaming_leg(device, rate=1e5, seconds=10.0, threads=32, window_us=2):
     """BASELINE.json configs[4]: sustained 100K req/s Poisson into a 256-pod pool through the native
     C++ host runtime (concurrent blocking Schedule callers -> micro-batches -> one C-ABI call per
     flush, snapshot re-packed every 50 ms); latency = completion - scheduled arrival."""
@@ -202,56 +256,61 @@ def streaming_leg(device, rate=1e5, seconds=3.0, threads=32, window_us=2):
         sched.close()
         prov.close()
     return {"workload": f"C5: {rate:.0f} req/s Poisson for {seconds:.0f} s into P={c['P']} pods, A={c['A']} adapters",
-            "achieved_req_per_s": len(lat) / seconds, "latency_us": {
+            "achieved_req_per_s": len(lat) / seconds, "requests": int(len(lat)), "latency_us": {
                 "p50": float(np.percentile(lat, 50)), "p90": float(np.percentile(lat, 90)),
                 "p99": float(np.percentile(lat, 99)), "p99.9": float(np.percentile(lat, 99.9)),
                 "max": float(lat.max())},
             "errors": int(nerr), "caller_threads": threads, "batch_window_us": window_us,
             "batcher": "busy-polling thread, callers spin 100 us before blocking",
             "batches": st["batches"], "avg_batch": st["scheduled"] / max(st["batches"], 1),
-            "snapshot_refreshes": st["refreshes"]}
+            "snapshot_refreshes": st["refreshes"], "failed_refreshes": st.get("failed_refreshes", 0)}
 
 
 def run_reference(args, cfg, R):
     """--impl reference: the reference's CPU algorithm (oracle port; the Go original cannot be
-    built in this image) on the host cores, each step a bounded sample of the workload."""
+    built in this image) on the host cores — resolve (FetchModelData + RandomWeightedDraw +
+    IsCritical) + Scheduler.Schedule per request —, each step a bounded sample of the workload.
+    Loads nothing of the product: the inputs come from the numpy-only workload module."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     from oracle import binding as oracle
-    nthreads = oracle.hardware_threads()
-    snap = WL.make_snapshot(cfg["P"], cfg["A"])
-    reqs = WL.make_requests(min(R, 1 << 18), cfg["A"])
+    nthreads = oracle.usable_threads()
+    P, A = cfg["P"], cfg["A"]
+    snap = WL.make_snapshot(P, A)
+    models = WL.make_models(A)
+    ids = WL.make_model_requests(min(R, 1 << 18), A)
     pool = oracle.Pool(snap.pod_records())
-    names = snap.adapter_names()
-    probe = min(len(reqs), 64 * nthreads)
+    mo = oracle.Models(WL.model_records(models))
+    probe = min(len(ids), 64 * nthreads)
     t0 = time.perf_counter()
-    pool.schedule_batch(names, WL.UNKNOWN_MODEL, np.ascontiguousarray(reqs[:probe]), 1, False, nthreads)
+    mo.schedule_batch(pool, np.ascontiguousarray(ids[:probe]), 1, 0, nthreads)
     rate = probe / max(time.perf_counter() - t0, 1e-6)
     budget = 60.0
-    S = int(max(16 * nthreads, min(len(reqs), rate * budget / (args.steps + args.warmup))))
-    chunks = [np.ascontiguousarray(reqs[(i * S) % (len(reqs) - S + 1):][:S]) for i in range(args.steps + args.warmup)]
+    S = int(max(16 * nthreads, min(len(ids), rate * budget / (args.steps + args.warmup))))
+    chunks = [np.ascontiguousarray(ids[(i * S) % (len(ids) - S + 1):][:S]) for i in range(args.steps + args.warmup)]
     for i in range(args.warmup):
-        pool.schedule_batch(names, WL.UNKNOWN_MODEL, chunks[i], i, False, nthreads)
+        mo.schedule_batch(pool, chunks[i], i, 0, nthreads)
     t0 = time.perf_counter()
     for i in range(args.warmup, args.warmup + args.steps):
-        pool.schedule_batch(names, WL.UNKNOWN_MODEL, chunks[i], i, False, nthreads)
+        mo.schedule_batch(pool, chunks[i], i, 0, nthreads)
     dt = time.perf_counter() - t0
     value = S * args.steps / dt
-    sample = f"{S} requests per step drawn from the {args.workload} batch (P={cfg['P']}, A={cfg['A']})"
+    sample = (f"{S} model requests per step drawn from the {args.workload} batch (P={P}, A={A}): the rate does not "
+              f"depend on the batch size, the full R={R} per step would take {R / value:.0f} s")
+    loaded = sorted({os.path.basename(l.split()[-1]) for l in open("/proc/self/maps") if "/repo/" in l and ".so" in l})
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64+f64",
-        "data": "synthetic",
-        "config": {"workload": workload_label(args.workload, R, cfg["P"], cfg["A"]),
-                   "requests_per_gpu": R, "pods": cfg["P"], "adapters": cfg["A"],
-                   "note": "C restatement of the Go scheduler (Go toolchain absent): same tree, pointer "
-                           "slices, string-keyed ActiveModels maps, fresh slice per stage; all host threads"},
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "int64+f64",
+        "data": "synthetic", "config": base_config(args, R, P, A, max(args.gpus, 1)),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": nthreads, "kind": "port", "sample": sample,
-                         "cgroup_cpu_quota_cores": cpu_quota()},
+                         "hardware_threads": oracle.hardware_threads(),
+                         "cgroup_cpu_quota_cores": oracle.cpu_quota_cores(),
+                         "note": "C restatement of the Go scheduler (Go toolchain absent): same tree, pointer slices, "
+                                 "string-keyed ActiveModels maps, fresh slice per stage, resolve step included"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "gpu_launches": 0, "repo_libraries_loaded": loaded,
     }
     print(json.dumps(line))
     return 0
@@ -269,8 +328,7 @@ def main():
     import torch.distributed as dist
 
     from llm_instance_gateway_b200.engine import Engine
-    from llm_instance_gateway_b200.packer import PICK_DTYPE
-    from llm_instance_gateway_b200.sharding import broadcast_snapshot, max_over_ranks, shard_bounds
+    from llm_instance_gateway_b200.packer import MPICK_DTYPE, PICK_DTYPE, pack_models
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -283,143 +341,243 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     P, A = cfg["P"], cfg["A"]
     K, Wm = args.steps, max(args.warmup, 3)
-    R_total = R * world
+    R_full = R
     if args.scaling == "strong":
-        lo, hi = shard_bounds(R, rank, world)
-        R_total, R = R, hi - lo
+        R = R_full * (rank + 1) // world - R_full * rank // world
+    R_total = R * world if args.scaling == "weak" else R_full
 
-    eng = Engine(local_rank, max_pods=max(P, 1), max_adapters=A, max_batch=R)
-    stream = torch.cuda.Stream()
-
-    # --- snapshot: rank 0 packs it, one NCCL broadcast replicates it (the only exchange step) ---
-    snap = WL.make_snapshot(P, A) if rank == 0 or world == 1 else None
-    nbytes = int(__import__("llm_instance_gateway_b200._native", fromlist=["x"]).load().lig_snapshot_bytes(P, A))
-    if rank == 0:
-        blob = torch.from_numpy(snap.packed.blob()).to(dev)
-    else:
-        blob = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-    broadcast_snapshot(blob, src=0)
-    epoch = 1
-    with torch.cuda.stream(stream):
-        eng.upload_snapshot_device(epoch, P, A, blob.data_ptr(), stream.cuda_stream)
-    stream.synchronize()
-
-    # --- resident request batches: more distinct bytes than L2 so no step re-reads a cached batch
-    nb = max(4, -(-2 * L2_BYTES // (R * 24)))
-    nb = min(nb, 64)
-    if args.ring > 0:
-        nb = args.ring
-    host_batches = [WL.make_requests(R, A, seed=WL.REQUEST_SEED + 1000 * rank + b) for b in range(min(nb, 8))]
-    d_reqs, d_out = [], []
-    for b in range(nb):
-        base = torch.from_numpy(host_batches[b % len(host_batches)].view(np.uint8).reshape(-1)).to(dev)
-        if b >= len(host_batches):       # derive further distinct batches on the device
-            v = base.view(torch.int64).clone()
-            v[1::2] ^= (0x9E3779B97F4A7C15 * (b + 1)) & 0x7FFFFFFFFFFFFFFF   # new rand_key
-            v = v.view(torch.uint8).view(-1, 16).roll(shifts=b * 7919, dims=0).contiguous()
-            base = v.view(-1)
-        d_reqs.append(base)
-        d_out.append(torch.zeros(R * 8, dtype=torch.uint8, device=dev))
-    req_ptrs = [t.data_ptr() for t in d_reqs]
-    out_ptrs = [t.data_ptr() for t in d_out]
-
-    def launch_steps(first, count, seed0):
-        idx = [(first + i) % nb for i in range(count)]
-        eng.schedule_batches_device(epoch, seed0, [req_ptrs[i] for i in idx], R, [out_ptrs[i] for i in idx],
-                                    stream.cuda_stream)
-
-    # --- parity spot check on the exact bench inputs (oracle = checker, not the thing measured) ---
-    parity_n = 0
-    if rank == 0:
-        from oracle import binding as oracle
-        parity_n = min(R, 4096)
-        with torch.cuda.stream(stream):
-            launch_steps(0, 1, 123)
-        stream.synchronize()
-        got = d_out[0][: parity_n * 8].cpu().numpy().view(PICK_DTYPE)
-        want, _ = oracle.Pool(snap.pod_records()).schedule_batch(
-            snap.adapter_names(), WL.UNKNOWN_MODEL, np.ascontiguousarray(host_batches[0][:parity_n]), 123)
-        if not np.array_equal(got, want):
-            raise SystemExit("bench inputs: GPU picks differ from the oracle — refusing to time a wrong kernel")
+    def max_over_ranks(v):
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # --- device-resident throughput (value) -------------------------------------------------------
-    with torch.cuda.stream(stream):
-        launch_steps(0, Wm, 1)
-        # every distinct K-step window of the batch ring once, untimed: the library caches one CUDA
-        # graph per (buffers, shape) queue, so graph instantiation happens here, not in a timed region
-        for off in range(nb):
-            launch_steps(off, K, 7)
-    barrier()
+    eng = Engine(local_rank, max_pods=max(P, 1), max_adapters=A, max_batch=max(R_full, R))
+    stream = torch.cuda.Stream()
 
+    # --- the library's own communicator: rank 0's NCCL unique id travels as a 128-byte tensor ---
+    if world > 1:
+        uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(eng.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, src=0)
+        eng.comm_init_rank(world, rank, bytes(uid.cpu().numpy().tobytes()))
+
+    # --- snapshot: every rank can regenerate it (seeded) for its own parity check, but only rank
+    #     0's copy is uploaded: one in-library ncclBroadcast replicates it into every rank's slot ---
+    snap = WL.make_snapshot(P, A)
+    blob = torch.from_numpy(snap.packed.blob()).to(dev)     # only rank 0's is ever sent
+    epoch, scratch = 1, 2       # two resident epochs: the benchmarked one and a scratch one for refresh timings
+
+    def upload_tick(ep):
+        if world > 1:
+            eng.comm_upload_snapshot_device(ep, P, A, blob.data_ptr(), 0, stream.cuda_stream)
+        else:
+            eng.upload_snapshot_device(ep, P, A, blob.data_ptr(), stream.cuda_stream)
+
+    with torch.cuda.stream(stream):
+        upload_tick(epoch)
+    stream.synchronize()
+    models = WL.make_models(A)
+    pmodels = pack_models(models, snap.packed)
+    eng.upload_models(epoch, pmodels)
+    info = eng.pick_kernel_info(epoch)
+
+    # --- resident request batches: more distinct bytes than L2 so no step re-reads a cached batch
+    nb = max(4, -(-2 * L2_BYTES // (R * 24)))
+    nb = min(nb, 64)
+    if args.ring > 0:
+        nb = args.ring
+    host_batches = [WL.make_requests(R, A, seed=WL.REQUEST_SEED + 1000 * rank + b) for b in range(min(nb, 4))]
+
+    def resident_ring(host, n):
+        d_in, d_out = [], []
+        for b in range(n):
+            base = torch.from_numpy(host[b % len(host)].view(np.uint8).reshape(-1)).to(dev)
+            if b >= len(host):       # derive further distinct batches on the device
+                v = base.view(torch.int64).clone()
+                v[1::2] ^= (0x9E3779B97F4A7C15 * (b + 1)) & 0x7FFFFFFFFFFFFFFF   # new rand_key
+                base = v.view(torch.uint8).view(-1, 16).roll(shifts=b * 7919, dims=0).contiguous().view(-1)
+            d_in.append(base)
+            d_out.append(torch.zeros(len(host[0]) * 8, dtype=torch.uint8, device=dev))
+        return d_in, d_out
+
+    d_reqs, d_out = resident_ring(host_batches, nb)
+    req_ptrs = [t.data_ptr() for t in d_reqs]
+    out_ptrs = [t.data_ptr() for t in d_out]
+
+    def launch_steps(first, count, seed0, rp=None, op=None, Rn=None):
+        rp, op, Rn = rp or req_ptrs, op or out_ptrs, Rn or R
+        idx = [(first + i) % len(rp) for i in range(count)]
+        eng.schedule_batches_device(epoch, seed0, [rp[i] for i in idx], Rn, [op[i] for i in idx], stream.cuda_stream)
+
+    # --- parity on the exact bench inputs, EVERY rank, its WHOLE shard, before anything is timed:
+    #     the class-table oracle (fast) checks all R picks; the structure-preserving port (the
+    #     restatement pinned to the reference's golden vectors) checks the class-table oracle and
+    #     the GPU on a sample; the model-request path is checked against resolve + Schedule ---
+    from oracle import binding as oracle
+    pk = snap.packed
+    with torch.cuda.stream(stream):
+        launch_steps(0, 1, 123)
+    stream.synchronize()
+    got = d_out[0].cpu().numpy().view(PICK_DTYPE)
+    tab = oracle.ClassTable(pk.P, pk.A, pk.kv, pk.q, pk.n_active, pk.max_active, pk.bitmap,
+                            nthreads=max(1, oracle.usable_threads() // max(world, 1)))
+    want = tab.schedule_batch(host_batches[0], 123, max(1, oracle.usable_threads() // max(world, 1)))
+    parity_port = min(R, 4096)
+    pool = oracle.Pool(snap.pod_records())
+    want_port, _ = pool.schedule_batch(snap.adapter_names(), WL.UNKNOWN_MODEL,
+                                       np.ascontiguousarray(host_batches[0][:parity_port]), 123)
+    ok = np.array_equal(got, want) and np.array_equal(want[:parity_port], want_port)
+    model_ids0 = WL.make_model_requests(R, A, seed=WL.REQUEST_SEED + 1000 * rank)
+    d_mid = torch.from_numpy(model_ids0.view(np.uint8)).to(dev)
+    d_mout = torch.zeros(R * 4, dtype=torch.uint8, device=dev)
+    with torch.cuda.stream(stream):
+        eng.schedule_models_batches_device(epoch, 321, 0, [d_mid.data_ptr()], R, [d_mout.data_ptr()], stream.cuda_stream)
+    stream.synchronize()
+    mo = oracle.Models(WL.model_records(models))
+    want_m = mo.schedule_batch(pool, np.ascontiguousarray(model_ids0[:parity_port]), 321, 0)
+    got_m = d_mout.cpu().numpy().view(MPICK_DTYPE)
+    ok = ok and np.array_equal(got_m[:parity_port], want_m)
+    flag = torch.tensor([0 if ok else 1], device=dev)
+    if world > 1:
+        dist.all_reduce(flag)
+    if int(flag.item()):
+        raise SystemExit(f"rank {rank}: GPU picks differ from the oracle on the bench inputs — refusing to time a wrong kernel")
+    parity = {"ranks_checked": world, "picks_checked_per_rank": int(R), "checker": "class-table oracle (all picks)",
+              "port_sample_per_rank": int(parity_port), "model_requests_port_sample_per_rank": int(parity_port)}
+
+    # --- device-resident throughput ---------------------------------------------------------------
     def gate():
         """~50 us spin kernel enqueued BEFORE the start event: while it runs the host enqueues the
         start event and all K steps, so the timed region holds device work only, not the host's
         submission latency (the region is still bracketed by barrier + synchronize)."""
-        try:
-            torch.cuda._sleep(100_000)
-        except Exception:
-            pass
+        torch.cuda._sleep(100_000)
+
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def time_regions(fn, Kn, min_seconds, max_reps=2000):
+        """fn(rep) enqueues one Kn-step region; returns (median ms, min ms, max ms, reps)."""
+        times, spent, reps = [], 0.0, 0
+        while True:
+            barrier()
+            with torch.cuda.stream(stream):
+                gate()
+                ev0.record(stream)
+                fn(reps)
+                ev1.record(stream)
+            barrier()
+            times.append(max_over_ranks(ev0.elapsed_time(ev1)))
+            spent += times[-1] / 1e3
+            reps += 1
+            stop = torch.tensor([1 if (spent >= min_seconds or reps >= max_reps) else 0], device=dev)
+            if world > 1:
+                dist.broadcast(stop, src=0)
+            if int(stop.item()):
+                break
+        return float(np.median(times)), min(times), max(times), reps
+
+    with torch.cuda.stream(stream):
+        launch_steps(0, Wm, 1)
+        for off in range(min(nb, 3)):
+            launch_steps(off, K, 7)
+    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     launches0 = eng.kernel_launches
-    times, reps, spent = [], 0, 0.0
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    while True:
-        barrier()
-        with torch.cuda.stream(stream):
-            gate()
-            ev0.record(stream)
-            launch_steps(reps * K, K, 1000 + reps)
-            ev1.record(stream)
-        barrier()
-        times.append(max_over_ranks(ev0.elapsed_time(ev1), dev))
-        spent += times[-1] / 1e3
-        reps += 1
-        stop = torch.tensor([1 if (spent >= args.min_seconds or reps >= 2000) else 0], device=dev)
-        if world > 1:
-            dist.broadcast(stop, src=0)
-        if int(stop.item()):
-            break
+    ms_region, ms_min, ms_max, reps = time_regions(lambda r: launch_steps(r * K, K, 1000 + r), K, args.min_seconds)
     launches_per_region = (eng.kernel_launches - launches0) // reps
-    ms_region = float(np.median(times))
     value = R_total * K / (ms_region / 1e3)
 
     if args.timed_only:
         if rank == 0:
             sampler.stop()
             print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
-                              "ms_per_step": ms_region / K, "timed_only": True}))
+                              "ms_per_step": ms_region / K, "timed_only": True, "kernel": info}))
         eng.close()
         if world > 1:
             dist.destroy_process_group()
         return 0
 
-    # --- snapshot refresh cost and the every-step-rebuild variant --------------------------------
+    extras = {}
+    if not args.no_extras:
+        # K sensitivity: a region pays one launch + pipeline fill + drain
+        ks = {}
+        for Kn in (1, 20, 200):
+            if Kn == K:
+                ks[str(Kn)] = {"us_per_step": ms_region * 1e3 / K, "value": value}
+                continue
+            med, _, _, _ = time_regions(lambda r: launch_steps(r * Kn, Kn, 3000 + r), Kn, 0.15, 200)
+            ks[str(Kn)] = {"us_per_step": med * 1e3 / Kn, "value": R_total * Kn / (med / 1e3)}
+        extras["k_sweep"] = ks
+        # the C4 configuration as north_star words it: ONE batch of the workload's R requests
+        # sharded contiguously over the N GPUs (R/N per GPU per step)
+        Rs = R_full * (rank + 1) // world - R_full * rank // world
+        med, _, _, _ = time_regions(lambda r: launch_steps(r * K, K, 4000 + r, Rn=Rs), K, 0.2, 400)
+        extras["strong"] = {"value": R_full * K / (med / 1e3), "unit": UNIT, "requests_per_gpu": int(Rs),
+                            "us_per_step": med * 1e3 / K, "steps": K,
+                            "frac_of_peak_per_gpu": (24 * Rs) / (med * 1e-3 / K) / 1e9 / hbm_peak()[0],
+                            "note": f"one {R_full}-request batch per step, contiguous shards over {world} GPU(s)"}
+        # the per-tick cost at N GPUs: ncclBroadcast of the packed snapshot into the resident slot +
+        # class-table build + compaction, on the device (no host synchronisation)
+        for i in range(3):
+            with torch.cuda.stream(stream):
+                upload_tick(scratch)
+        med, _, _, _ = time_regions(lambda r: [upload_tick(scratch) for i in range(10)], 10, 0.05, 50)
+        extras["snapshot_tick"] = {"us": med * 1e3 / 10, "n_gpus": world,
+                                   "what": ("ncclBroadcast (in the library) + class-table build + compaction" if world > 1
+                                            else "device-to-device copy + class-table build + compaction"),
+                                   "bytes": int(snap.packed.blob().nbytes)}
+        barrier()
+        # adapter-distribution sensitivity: uniform adapters instead of Zipf(1.1)
+        rng = np.random.default_rng(99 + rank)
+        uni = [h.copy() for h in host_batches[:2]]
+        for h in uni:
+            h["adapter_id"] = rng.integers(0, A + 1, len(h)).astype(np.int32)
+        u_in, u_out = resident_ring(uni, nb)
+        urp, uop = [t.data_ptr() for t in u_in], [t.data_ptr() for t in u_out]
+        with torch.cuda.stream(stream):
+            launch_steps(0, K, 5, urp, uop)
+        med, _, _, _ = time_regions(lambda r: launch_steps(r * K, K, 5000 + r, urp, uop), K, 0.2, 400)
+        extras["adapter_dist_uniform"] = {"value": R_total * K / (med / 1e3), "us_per_step": med * 1e3 / K,
+                                          "note": "adapter ids uniform over [0, A] instead of Zipf(1.1)"}
+        del u_in, u_out
+        # model requests (the resolve step fused into the pick): 4 B in + 4 B out per decision
+        mids = [WL.make_model_requests(R, A, seed=WL.REQUEST_SEED + 1000 * rank + b) for b in range(2)]
+        nbm = min(64, max(4, -(-2 * L2_BYTES // (R * 8))))
+        m_in = [torch.from_numpy(np.roll(mids[b % 2], b * 7919).view(np.uint8)).to(dev) for b in range(nbm)]
+        m_out = [torch.zeros(R * 4, dtype=torch.uint8, device=dev) for _ in range(nbm)]
+        mip, mop = [t.data_ptr() for t in m_in], [t.data_ptr() for t in m_out]
+
+        def launch_models(first, count, seed0):
+            idx = [(first + i) % nbm for i in range(count)]
+            eng.schedule_models_batches_device(epoch, seed0, 0, [mip[i] for i in idx], R, [mop[i] for i in idx],
+                                               stream.cuda_stream)
+        with torch.cuda.stream(stream):
+            launch_models(0, K, 5)
+        med, _, _, _ = time_regions(lambda r: launch_models(r * K, K, 6000 + r), K, 0.2, 400)
+        extras["model_requests"] = {"value": R_total * K / (med / 1e3), "unit": UNIT, "us_per_step": med * 1e3 / K,
+                                    "bytes_per_decision": 8, "hbm_gbs": 8 * R / (med * 1e-3 / K) / 1e9,
+                                    "note": "lig_schedule_models_batches_device: model lookup + weighted target draw + "
+                                            "criticality + Schedule in one pass; issue-bound, not HBM-bound"}
+        del m_in, m_out
+
+    # --- snapshot refresh cost and the direct-scan kernel (transparency figures) ------------------
     with torch.cuda.stream(stream):
         for i in range(3):
-            eng.upload_snapshot_device(epoch, P, A, blob.data_ptr(), stream.cuda_stream)
+            eng.upload_snapshot_device(scratch, P, A, blob.data_ptr(), stream.cuda_stream)
         ev0.record(stream)
         for i in range(20):
-            eng.upload_snapshot_device(epoch, P, A, blob.data_ptr(), stream.cuda_stream)
+            eng.upload_snapshot_device(scratch, P, A, blob.data_ptr(), stream.cuda_stream)
         ev1.record(stream)
     barrier()
     snapshot_build_us = ev0.elapsed_time(ev1) / 20 * 1e3
-    with torch.cuda.stream(stream):
-        ev0.record(stream)
-        for i in range(min(K, 50)):
-            eng.upload_snapshot_device(epoch, P, A, blob.data_ptr(), stream.cuda_stream)
-            launch_steps(i, 1, 5000 + i)
-        ev1.record(stream)
-    barrier()
-    value_rebuild = R_total / (max_over_ranks(ev0.elapsed_time(ev1) / min(K, 50), dev) / 1e3)
-
-    # --- direct-scan kernel (per-request tree walk, no class tables): secondary figure -------------
     Rs = min(R, 1 << 15)
     with torch.cuda.stream(stream):
         eng.schedule_scan_device(epoch, 1, req_ptrs[0], Rs, out_ptrs[0], 0, stream.cuda_stream)
@@ -428,105 +586,104 @@ def main():
             eng.schedule_scan_device(epoch, 2 + i, req_ptrs[1 % nb], Rs, out_ptrs[1 % nb], 0, stream.cuda_stream)
         ev1.record(stream)
     barrier()
-    scan_ms = ev0.elapsed_time(ev1) / 3
-    scan_value = Rs / (scan_ms / 1e3)
+    scan_value = Rs / (ev0.elapsed_time(ev1) / 3 / 1e3)
 
-    # --- e2e: host buffers through the public C-ABI call, snapshot refresh included every step ----
-    lib_reqs = [torch.from_numpy(hb.view(np.uint8).reshape(-1)).pin_memory() for hb in host_batches[:4]]
-    pin_out = torch.zeros(R * 8, dtype=torch.uint8).pin_memory()
-    if rank == 0 or world == 1:
-        packed = snap.packed
-    else:
-        packed = WL.make_snapshot(P, A).packed
+    # --- e2e: host buffers through the public C-ABI calls, refresh tick charged to every step -----
+    # (a) the model-request call (what the Go adapter makes per flush): 4-byte model ids in, 4-byte
+    #     picks out, page-locked buffers read / written over PCIe in place;
+    # (b) the 16-byte descriptor call of round 1 (requests resolved on the host).
     e2e_steps = max(3, min(K, 50))
-    for i in range(3):
-        eng.upload_snapshot(epoch + 1, packed)
-        eng.schedule_batch_ptr(epoch + 1, i, lib_reqs[i % len(lib_reqs)].data_ptr(), R, pin_out.data_ptr())
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(e2e_steps):
-        eng.upload_snapshot(epoch + 1, packed)        # the 50 ms refresh tick, charged to every step
-        eng.schedule_batch_ptr(epoch + 1, 100 + i, lib_reqs[i % len(lib_reqs)].data_ptr(), R, pin_out.data_ptr())
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    e2e_value = R_total * e2e_steps / max_over_ranks(e2e_s, dev)
-    # the same loop without the per-step snapshot refresh (the real cadence is one refresh per
-    # ~100 such batches): informational, not the headline
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(e2e_steps):
-        eng.schedule_batch_ptr(epoch + 1, 200 + i, lib_reqs[i % len(lib_reqs)].data_ptr(), R, pin_out.data_ptr())
-    torch.cuda.synchronize()
-    e2e_resident_value = R_total * e2e_steps / max_over_ranks(time.perf_counter() - t0, dev)
+    packed = snap.packed
+    mid_pin = [torch.from_numpy(WL.make_model_requests(R, A, seed=WL.REQUEST_SEED + 77 + b).view(np.uint8)).pin_memory()
+               for b in range(4)]
+    mout_pin = torch.zeros(R * 4, dtype=torch.uint8).pin_memory()
+    req_pin = [torch.from_numpy(hb.view(np.uint8).reshape(-1)).pin_memory() for hb in host_batches[:4]]
+    out_pin = torch.zeros(R * 8, dtype=torch.uint8).pin_memory()
+    ep2 = scratch
+
+    def e2e_models(i, refresh):
+        if refresh:
+            eng.upload_snapshot(ep2, packed)          # the 50 ms refresh tick, charged to every step
+            eng.upload_models(ep2, pmodels)
+        eng.schedule_models_batch_ptr(ep2, 100 + i, 0, mid_pin[i % 4].data_ptr(), R, mout_pin.data_ptr())
+
+    def e2e_descr(i, refresh):
+        if refresh:
+            eng.upload_snapshot(ep2, packed)
+        eng.schedule_batch_ptr(ep2, 100 + i, req_pin[i % 4].data_ptr(), R, out_pin.data_ptr())
+
+    def e2e_rate(fn, refresh):
+        eng.upload_snapshot(ep2, packed)
+        eng.upload_models(ep2, pmodels)
+        for i in range(3):
+            fn(i, refresh)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            fn(i, refresh)
+        torch.cuda.synchronize()
+        return R_total * e2e_steps / max_over_ranks(time.perf_counter() - t0)
+
+    e2e_value = e2e_rate(e2e_models, True)
+    e2e_resident = e2e_rate(e2e_models, False)
+    e2e_descr_value = e2e_rate(e2e_descr, True)
+    e2e_descr_resident = e2e_rate(e2e_descr, False)
+    # the e2e result is a real answer: compare the last model-request step with the oracle
+    want_last = mo.schedule_batch(pool, np.ascontiguousarray(
+        np.frombuffer(mid_pin[(e2e_steps - 1) % 4].numpy(), dtype=np.uint32)[:parity_port]), 100 + e2e_steps - 1, 0)
+    if not np.array_equal(mout_pin.numpy().view(MPICK_DTYPE)[:parity_port], want_last):
+        raise SystemExit("e2e result differs from the oracle")
     clocks = sampler.stop() if rank == 0 else None
 
     if rank == 0:
         peak, peak_src = hbm_peak()
-        # algorithmic bytes of one step: 24 B per decision + the snapshot S(P, A) once per LAUNCH
-        # (a merged queue launch serves K steps with one pass over the class tables)
+        nbytes = int(packed.blob().nbytes)
+        # algorithmic bytes of one step: 24 B per decision + the tables once per LAUNCH (a queue of K
+        # steps is one launch; its CTAs pull the compact tables into shared memory once)
         snap_share = (16 * P + 4 * A * ((P + 31) // 32)) * min(1.0, max(launches_per_region, 1) / K)
         alg_bytes = int(24 * R + snap_share)
         launch_s = ms_region / 1e3 / K
         achieved = alg_bytes / launch_s / 1e9
+        traffic, traffic_note = committed_traffic(args.workload, info, K // max(launches_per_region, 1))
+        cfgd = base_config(args, R, P, A, world)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": ms_region / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
-            "dtype": "int32+u64+f64", "data": "synthetic",
-            "config": {
-                "workload": workload_label(args.workload, R, P, A),
-                "requests_per_gpu": R, "pods": P, "adapters": A, "parallelism": f"request-sharded x{world}",
+            "dtype": "int32+u64+f64", "data": "synthetic", "config": cfgd,
+            "details": {
                 "l2": f"{nb} distinct resident batches ({nb * R * 24 / 2**20:.0f} MiB in+out) cycled: "
                       "inputs larger than the 126 MB L2",
-                "timed_region_repeats": reps, "region_ms_min_med_max": [min(times), ms_region, max(times)],
-                "snapshot": "resident (tables built at upload, once per refresh tick); see with_snapshot_rebuild",
-            },
+                "timed_region_repeats": reps, "region_ms_min_med_max": [ms_min, ms_region, ms_max],
+                "snapshot": "resident (tables built at upload, once per refresh tick)",
+                "kernel": info},
             "e2e": {"value": e2e_value, "unit": UNIT,
-                    "h2d_bytes_per_step": 16 * R + nbytes, "d2h_bytes_per_step": 8 * R,
-                    "steps": e2e_steps, "value_snapshot_resident": e2e_resident_value,
-                    "note": "lig_upload_snapshot + lig_schedule_batch per step; the pick kernel reads the "
-                            "pinned host descriptors and writes the pinned host picks over PCIe in place"},
+                    "h2d_bytes_per_step": 4 * R + nbytes + int(pmodels.target_offsets.nbytes + 8 * pmodels.n_models),
+                    "d2h_bytes_per_step": 4 * R, "steps": e2e_steps, "value_snapshot_resident": e2e_resident,
+                    "call": "lig_upload_snapshot + lig_upload_models + lig_schedule_models_batch per step: 4-byte model "
+                            "ids in, 4-byte picks out, the kernel reads / writes the pinned host buffers over PCIe in place",
+                    "descriptor_call": {"value": e2e_descr_value, "value_snapshot_resident": e2e_descr_resident,
+                                        "h2d_bytes_per_step": 16 * R + nbytes, "d2h_bytes_per_step": 8 * R,
+                                        "call": "lig_upload_snapshot + lig_schedule_batch (16-byte descriptors resolved on "
+                                                "the host, 8-byte picks): the round-1 e2e figure"}},
             "gpu_launches": int(launches_per_region),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak,
-                         "traffic": committed_traffic(args.workload, K // max(launches_per_region, 1)),
-                         "kernel": ("lig_pick_queue_kernel (K steps per launch)" if launches_per_region < K
-                                    else "lig_pick_stream_kernel"),
+                         "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note,
+                         "kernel": f"{info['kernel']} (K steps per launch)" if launches_per_region < K else info["kernel"],
                          "algorithmic_bytes_per_step": alg_bytes,
                          "algorithmic_bytes_per_launch": int(alg_bytes * K / max(launches_per_region, 1)),
                          "step_us": launch_s * 1e6, "launch_us": ms_region * 1e3 / max(launches_per_region, 1),
                          "peak_source": peak_src},
             "clocks": clocks,
             "snapshot_build_us": snapshot_build_us,
-            "with_snapshot_rebuild": {"value": value_rebuild, "unit": UNIT,
-                                      "note": "every step re-uploads the snapshot and rebuilds all class tables"},
             "direct_scan": {"value": scan_value, "unit": UNIT, "pod_evals_per_s": scan_value * P,
                             "requests": Rs, "note": "lig_scan_kernel: per-request tree walk, no class tables"},
-            "parity_checked": parity_n,
+            "parity": parity,
         }
+        line.update(extras)
         if world == 1 and not args.no_streaming:
-            line["streaming"] = streaming_leg(local_rank)
+            line["streaming"] = streaming_leg(local_rank, seconds=args.stream_seconds)
         if world == 1 and not args.no_cpu_baseline:
-            from oracle import binding as oracle
-            nthreads = oracle.hardware_threads()
-            v, sample = cpu_reference_rate(snap, host_batches[0], 123, nthreads, args.cpu_seconds)
-            v1, sample1 = cpu_reference_rate(snap, host_batches[0], 123, 1, min(args.cpu_seconds, 3.0))
-            from oracle import binding as _ob
-            pk = snap.packed
-            n_opt = min(R, 1 << 19)
-            t0 = time.perf_counter()
-            _ob.soa_schedule_batch(pk.P, pk.A, pk.kv, pk.q, pk.n_active, pk.max_active, pk.bitmap,
-                                   np.ascontiguousarray(host_batches[0][:n_opt]), 123, False, nthreads)
-            v_opt = n_opt / (time.perf_counter() - t0)
-            line["cpu_baseline"] = {
-                "value": v, "unit": UNIT, "cores": nthreads, "kind": "port",
-                "sample": f"first {sample} requests of batch 0 of the same workload",
-                "single_thread": {"value": v1, "sample": sample1},
-                "optimised_cpu": {"value": v_opt, "cores": nthreads, "sample": n_opt,
-                                  "note": "fairness datapoint (oracle/lig_oracle_soa.c): same per-request tree "
-                                          "walk on columns + adapter bitmaps + mask words, no allocation"},
-                "cgroup_cpu_quota_cores": cpu_quota(),
-                "note": "C restatement of the Go scheduler with the reference's data structures "
-                        "(Go toolchain absent from the image)"}
+            line["cpu_baseline"] = cpu_arms(snap, models, host_batches[0], model_ids0, 123, args.cpu_seconds)
         print(json.dumps(line))
     eng.close()
     if world > 1:

@@ -2,6 +2,8 @@
 #include "lig_host.hpp"
 
 #include <algorithm>
+#include <climits>
+#include <cstdio>
 #include <cstring>
 #include <random>
 
@@ -76,10 +78,43 @@ Scheduler::~Scheduler() {
 }
 
 // One pack per refresh tick replaces the per-request AllPodMetrics() of scheduler.go:114-115.
+// A failed refresh keeps the previous snapshot — like a failed scrape keeps stale metrics
+// (backend/provider.go:151-156) — but never silently: it is counted and its reason kept.
 Status Scheduler::Refresh() {
+  Status st = RefreshImpl();
+  if (!st.ok()) {
+    std::lock_guard<std::mutex> sk(stats_mu_);
+    stats_.failed_refreshes++;
+    last_refresh_error_ = st.message;
+    fprintf(stderr, "lig: snapshot refresh failed, keeping the previous one: %s\n", st.message.c_str());
+  }
+  return st;
+}
+
+std::string Scheduler::last_refresh_error() const {
+  std::lock_guard<std::mutex> sk(stats_mu_);
+  return last_refresh_error_;
+}
+
+Status Scheduler::RefreshImpl() {
   std::lock_guard<std::mutex> rk(refresh_mu_);
   const auto t_begin = std::chrono::steady_clock::now();
   auto pods = pmp_->AllPodMetrics();
+  // A pod whose metrics do not fit the device record (WaitingQueueSize outside int32,
+  // len(ActiveModels) above the record's limit) is left out of this snapshot and counted; one bad
+  // scrape must not freeze the whole pool on a stale snapshot.
+  uint64_t excluded = 0;
+  {
+    size_t keep = 0;
+    for (size_t i = 0; i < pods.size(); ++i) {
+      const auto& m = pods[i]->metrics;
+      const bool fits = m.WaitingQueueSize >= INT32_MIN && m.WaitingQueueSize <= INT32_MAX &&
+                        m.ActiveModels.size() <= (size_t)LIG_MAX_ADAPTERS;
+      if (fits) pods[keep++] = pods[i];
+      else ++excluded;
+    }
+    pods.resize(keep);
+  }
   const int P = (int)pods.size();
   const int W = (P + 31) / 32;
   auto snap = std::make_shared<Snapshot>();
@@ -149,6 +184,7 @@ Status Scheduler::Refresh() {
   const auto t_done = std::chrono::steady_clock::now();
   std::lock_guard<std::mutex> sk(stats_mu_);
   stats_.refreshes++;
+  stats_.excluded_pods = excluded;
   stats_.last_pack_us = std::chrono::duration<double, std::micro>(t_packed - t_begin).count();
   stats_.last_upload_us = std::chrono::duration<double, std::micro>(t_done - t_packed).count();
   return Status{};
@@ -160,8 +196,7 @@ void Scheduler::RefresherLoop() {
     cv_.wait_for(lk, opt_.refresh_interval, [&] { return stop_; });
     if (stop_) break;
     lk.unlock();
-    Refresh();   // a failed refresh keeps the previous snapshot, like a failed scrape keeps stale
-                 // metrics (backend/provider.go:151-156)
+    Refresh();   // failures are counted and logged there
     lk.lock();
   }
 }
@@ -186,6 +221,13 @@ Status Scheduler::Schedule(const LLMRequest& req, backend::Pod* targetPod) {
     }
   }
   w.done.wait(0, std::memory_order_acquire);
+  // the notifier may still be inside notify_one() on this stack object: leave only once it says
+  // it is finished (done == 2); a handful of spins at most
+  while (w.done.load(std::memory_order_acquire) != 2) {
+#if defined(__x86_64__)
+    __builtin_ia32_pause();
+#endif
+  }
   if (w.status.ok() && targetPod) *targetPod = std::move(w.pod);
   return w.status;
 }
@@ -284,6 +326,7 @@ void Scheduler::Flush(std::vector<Waiter*>& batch) {
       Waiter* w = batch[done + i];
       w->done.store(1, std::memory_order_release);
       w->done.notify_one();
+      w->done.store(2, std::memory_order_release);   // last access: the caller may now destroy *w
     }
     done += (size_t)n;
   }

@@ -110,6 +110,8 @@ struct Stats {
   uint64_t max_batch = 0;      // largest batch flushed
   uint64_t refreshes = 0;      // snapshots uploaded
   uint64_t stale_retries = 0;  // batches re-resolved after LIG_ERR_STALE_EPOCH
+  uint64_t failed_refreshes = 0;   // Refresh() calls that kept the previous snapshot (see last_refresh_error)
+  uint64_t excluded_pods = 0;      // pods left out of the last snapshot: a metric did not fit the device record
   double last_pack_us = 0;     // last Refresh: provider slice -> columns + bitmap (host)
   double last_upload_us = 0;   // last Refresh: lig_upload_snapshot (H2D + class tables)
 };
@@ -129,8 +131,12 @@ class Scheduler {
 
   // Re-read the provider and upload a new snapshot epoch (call on every metrics refresh).
   Status Refresh();
+ private:
+  Status RefreshImpl();
+ public:
 
   Stats stats() const;
+  std::string last_refresh_error() const;
 
  private:
   friend Status NewScheduler(std::shared_ptr<PodMetricsProvider>, const Options&,
@@ -153,6 +159,8 @@ class Scheduler {
   };
   std::shared_ptr<InternTable> intern_;
   std::vector<PodMemo> memo_;
+  // Lives on the caller's stack.  `done` goes 0 -> 1 (result published, the caller may read it)
+  // -> 2 (the notifier will not touch the Waiter again, the caller may return and destroy it).
   struct Waiter {
     const LLMRequest* req = nullptr;
     Status status;
@@ -188,6 +196,7 @@ class Scheduler {
 
   mutable std::mutex stats_mu_;
   Stats stats_;
+  std::string last_refresh_error_;
 };
 
 // NewScheduler                                                        scheduler.go:93-99

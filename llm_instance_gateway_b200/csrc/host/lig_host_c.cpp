@@ -124,10 +124,10 @@ int ligh_refresh(ligh_scheduler* s, char* err, int err_cap) {
   return st.code;
 }
 
-void ligh_stats(ligh_scheduler* s, uint64_t out[5]) {
+void ligh_stats(ligh_scheduler* s, uint64_t out[7]) {
   scheduling::Stats st = s->sched->stats();
   out[0] = st.scheduled; out[1] = st.batches; out[2] = st.max_batch; out[3] = st.refreshes;
-  out[4] = st.stale_retries;
+  out[4] = st.stale_retries; out[5] = st.failed_refreshes; out[6] = st.excluded_pods;
 }
 
 void ligh_refresh_timing(ligh_scheduler* s, double out[2]) {

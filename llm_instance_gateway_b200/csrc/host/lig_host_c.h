@@ -33,7 +33,7 @@ void ligh_scheduler_free(ligh_scheduler*);
 int ligh_schedule(ligh_scheduler*, const char* model, const char* resolved_target_model, int critical,
                   char* name, int name_cap, char* addr, int addr_cap, char* err, int err_cap);
 int ligh_refresh(ligh_scheduler*, char* err, int err_cap);
-void ligh_stats(ligh_scheduler*, uint64_t out[5]); /* scheduled, batches, max_batch, refreshes, stale_retries */
+void ligh_stats(ligh_scheduler*, uint64_t out[7]); /* scheduled, batches, max_batch, refreshes, stale_retries */
 void ligh_refresh_timing(ligh_scheduler*, double out[2]); /* last Refresh: host pack us, lig_upload_snapshot us */
 
 /* n_threads caller threads each issue `per_thread` blocking Schedule calls (model i of the

@@ -141,9 +141,10 @@ class HostScheduler:
             raise HostSchedulerError(err.value.decode())
 
     def stats(self) -> dict:
-        out = (C.c_uint64 * 5)()
+        out = (C.c_uint64 * 7)()
         self._lib.ligh_stats(self._s, out)
-        return dict(zip(("scheduled", "batches", "max_batch", "refreshes", "stale_retries"), map(int, out)))
+        return dict(zip(("scheduled", "batches", "max_batch", "refreshes", "stale_retries", "failed_refreshes",
+                         "excluded_pods"), map(int, out)))
 
     def refresh_timing(self) -> dict:
         out = (C.c_double * 2)()

@@ -168,6 +168,6 @@ def make_model_requests(R: int, A: int, seed: int = REQUEST_SEED) -> np.ndarray:
     return np.ascontiguousarray(ids, dtype=np.uint32)
 
 
-def oracle_model_records(models: List[InferenceModel]) -> List[dict]:
+def model_records(models: List[InferenceModel]) -> List[dict]:
     return [dict(name=m.Spec.ModelName, critical=(m.Spec.Criticality == CRITICAL),
                  targets=[(t.Name, t.Weight) for t in m.Spec.TargetModels]) for m in models]

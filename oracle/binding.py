@@ -74,7 +74,7 @@ def load() -> C.CDLL:
     lib.lig_oracle_weighted_select.argtypes = [vp, i32, C.c_int32]
     lib.lig_oracle_random_weighted_draw.argtypes = [vp, i32, u64]
     lib.lig_oracle_resolve.argtypes = [vp, i32, u64, u64, C.POINTER(C.c_char_p), C.POINTER(i32), C.POINTER(i32)]
-    lib.lig_oracle_schedule_models_batch.argtypes = [vp, vp, vp, i32, u64, u64, vp]
+    lib.lig_oracle_schedule_models_batch.argtypes = [vp, vp, vp, i32, u64, u64, vp, i32]
     lib.lig_oracle_splitmix64_next.argtypes = [C.POINTER(u64)]
     lib.lig_oracle_splitmix64_next.restype = u64
     lib.lig_oracle_int31n.argtypes = [C.POINTER(u64), C.c_int32]
@@ -183,6 +183,22 @@ def hardware_threads() -> int:
     return int(load().lig_oracle_hardware_threads())
 
 
+def cpu_quota_cores():
+    """cgroup v2 CPU quota of this container in cores (None = unlimited)."""
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        return None if quota == "max" else float(quota) / float(period)
+    except Exception:
+        return None
+
+
+def usable_threads() -> int:
+    """min(hardware threads, cgroup quota): more threads than the quota only adds contention."""
+    n = hardware_threads()
+    q = cpu_quota_cores()
+    return max(1, min(n, int(q + 0.5))) if q else n
+
+
 def splitmix64_stream(state: int, n: int) -> List[int]:
     lib = load()
     st = C.c_uint64(state)
@@ -271,11 +287,12 @@ class Models:
         rc = self._lib.lig_oracle_resolve(self._m, model, seed, rand_key, C.byref(name), C.byref(crit), C.byref(tgt))
         return rc, (name.value.decode() if rc == 0 else None), bool(crit.value), tgt.value
 
-    def schedule_batch(self, pool: "Pool", model_ids: np.ndarray, seed: int, first_index: int = 0) -> np.ndarray:
+    def schedule_batch(self, pool: "Pool", model_ids: np.ndarray, seed: int, first_index: int = 0,
+                       nthreads: int = 1) -> np.ndarray:
         assert model_ids.dtype == np.uint32 and model_ids.flags.c_contiguous
         R = int(model_ids.shape[0])
         out = np.zeros(R, dtype=MPICK_DTYPE)
         rc = self._lib.lig_oracle_schedule_models_batch(pool._p, self._m, model_ids.ctypes.data if R else None, R,
-                                                        seed, first_index, out.ctypes.data if R else None)
+                                                        seed, first_index, out.ctypes.data if R else None, nthreads)
         assert rc == 0
         return out

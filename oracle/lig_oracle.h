@@ -130,7 +130,7 @@ int lig_oracle_resolve(const lig_oracle_models*, int model, uint64_t seed, uint6
                        const char** resolved, int* critical, int* target_idx);
 int lig_oracle_schedule_models_batch(const lig_oracle_pool*, const lig_oracle_models*,
                                      const uint32_t* model_ids, int R, uint64_t seed,
-                                     uint64_t first_index, lig_oracle_mpick* out);
+                                     uint64_t first_index, lig_oracle_mpick* out, int nthreads);
 
 /* The pick primitives, exposed for known-answer tests. */
 uint64_t lig_oracle_splitmix64_next(uint64_t* state);

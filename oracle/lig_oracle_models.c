@@ -21,6 +21,7 @@
  * target the Go loop selects for randomVal = v, for every v in [0, sum)), and the distribution.
  */
 #define _GNU_SOURCE
+#include <pthread.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -122,29 +123,62 @@ int lig_oracle_resolve(const lig_oracle_models* s, int model, uint64_t seed, uin
 }
 
 /* R requests given as model ids; request i has rand_key = first_index + i.  Resolve, then
- * Scheduler.Schedule on the port (lig_oracle_schedule), one request at a time. */
-int lig_oracle_schedule_models_batch(const lig_oracle_pool* pool, const lig_oracle_models* s,
-                                     const uint32_t* model_ids, int R, uint64_t seed,
-                                     uint64_t first_index, lig_oracle_mpick* out) {
-  if (!pool || !s || R < 0 || (R > 0 && (!model_ids || !out))) return -1;
-  for (int i = 0; i < R; ++i) {
-    const uint64_t key = first_index + (uint64_t)i;
+ * Scheduler.Schedule on the port (lig_oracle_schedule), one request at a time; nthreads > 1
+ * partitions the requests statically over that many pthreads (one goroutine per request in the
+ * reference, handlers/server.go:51). */
+typedef struct {
+  const lig_oracle_pool* pool;
+  const lig_oracle_models* s;
+  const uint32_t* model_ids;
+  lig_oracle_mpick* out;
+  int lo, hi;
+  uint64_t seed, first_index;
+} models_job;
+
+static void* models_worker(void* arg) {
+  models_job* j = (models_job*)arg;
+  for (int i = j->lo; i < j->hi; ++i) {
+    const uint64_t key = j->first_index + (uint64_t)i;
     const char* name = NULL;
     int critical = 0, target = 255;
-    const int rs = model_ids[i] <= 0x7fffffffu
-                       ? lig_oracle_resolve(s, (int)model_ids[i], seed, key, &name, &critical, &target) : 3;
-    out[i].pod_idx = -1;
-    out[i].target_idx = (uint8_t)target;
+    const int rs = j->model_ids[i] <= 0x7fffffffu
+                       ? lig_oracle_resolve(j->s, (int)j->model_ids[i], j->seed, key, &name, &critical, &target) : 3;
+    j->out[i].pod_idx = -1;
+    j->out[i].target_idx = (uint8_t)target;
     if (rs != 0) {
-      out[i].status = (uint8_t)rs;
-      out[i].target_idx = 255;
+      j->out[i].status = (uint8_t)rs;
+      j->out[i].target_idx = 255;
       continue;
     }
     int32_t pod = -1;
     int n = 0;
-    const int st = lig_oracle_schedule(pool, name, critical, seed, key, &pod, &n);
-    out[i].status = (uint8_t)st;
-    out[i].pod_idx = (int16_t)(st == LIGO_OK ? pod : -1);
+    const int st = lig_oracle_schedule(j->pool, name, critical, j->seed, key, &pod, &n);
+    j->out[i].status = (uint8_t)st;
+    j->out[i].pod_idx = (int16_t)(st == LIGO_OK ? pod : -1);
   }
+  return NULL;
+}
+
+int lig_oracle_schedule_models_batch(const lig_oracle_pool* pool, const lig_oracle_models* s,
+                                     const uint32_t* model_ids, int R, uint64_t seed,
+                                     uint64_t first_index, lig_oracle_mpick* out, int nthreads) {
+  if (!pool || !s || R < 0 || (R > 0 && (!model_ids || !out))) return -1;
+  if (nthreads < 1) nthreads = 1;
+  if (nthreads > R) nthreads = R > 0 ? R : 1;
+  models_job* jobs = (models_job*)calloc((size_t)nthreads, sizeof(models_job));
+  pthread_t* th = (pthread_t*)calloc((size_t)nthreads, sizeof(pthread_t));
+  for (int t = 0; t < nthreads; ++t) {
+    models_job j = {pool, s, model_ids, out, (int)((int64_t)R * t / nthreads),
+                    (int)((int64_t)R * (t + 1) / nthreads), seed, first_index};
+    jobs[t] = j;
+  }
+  if (nthreads == 1) {
+    models_worker(&jobs[0]);
+  } else {
+    for (int t = 0; t < nthreads; ++t) pthread_create(&th[t], NULL, models_worker, &jobs[t]);
+    for (int t = 0; t < nthreads; ++t) pthread_join(th[t], NULL);
+  }
+  free(jobs);
+  free(th);
   return 0;
 }

@@ -19,7 +19,7 @@ def setup(oracle, cfg, snap_seed=WL.SNAPSHOT_SEED):
     snap = WL.make_snapshot(c["P"], c["A"], seed=snap_seed)
     models = WL.make_models(c["A"])
     pm = pack_models(models, snap.packed)
-    return c, snap, models, pm, oracle.Pool(snap.pod_records()), oracle.Models(WL.oracle_model_records(models))
+    return c, snap, models, pm, oracle.Pool(snap.pod_records()), oracle.Models(WL.model_records(models))
 
 
 @pytest.mark.parametrize("cfg", ["C2", "C3", "C5"])
@@ -115,7 +115,7 @@ def test_model_table_validation_and_edge_tables(oracle):
               mk("zeros-inside", None, [(WL.adapter_name(0), 0), (WL.adapter_name(1), 3), ("nowhere", 0), (WL.adapter_name(2), 4)])]
     pm = pack_models(models, P)
     assert pm.present.tolist() == [1, 1, 0, 1, 1, 1]
-    recs = WL.oracle_model_records(models)
+    recs = WL.model_records(models)
     recs[2] = None
     mo, pool = oracle.Models(recs), oracle.Pool(snap.pod_records())
     ids = np.tile(np.arange(8, dtype=np.uint32), 4000)

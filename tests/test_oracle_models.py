@@ -135,7 +135,7 @@ def test_models_batch_equals_resolve_then_schedule(oracle):
     A, P = 8, 64
     snap = WL.make_snapshot(P, A, seed=3)
     models = WL.make_models(A)
-    mo = oracle.Models(WL.oracle_model_records(models))
+    mo = oracle.Models(WL.model_records(models))
     pool = oracle.Pool(snap.pod_records())
     ids = WL.make_model_requests(3000, A, seed=4)
     out = mo.schedule_batch(pool, ids, 11, first_index=1000)
