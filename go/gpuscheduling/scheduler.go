@@ -68,9 +68,10 @@ type GPUScheduler struct {
 	snap   *packedSnapshot
 	epoch  uint64
 
-	queue chan *waiter
-	stop  chan struct{}
-	wg    sync.WaitGroup
+	queue     chan *waiter
+	stop      chan struct{}
+	wg        sync.WaitGroup
+	closeOnce sync.Once
 }
 
 // NewGPUScheduler mirrors scheduling.NewScheduler(pmp) (scheduler.go:93-99).
@@ -106,16 +107,26 @@ func NewGPUScheduler(pmp scheduling.PodMetricsProvider, opt Options) (*GPUSchedu
 	return g, nil
 }
 
+// Close stops the batcher and the refresher, answers every request that was still queued (or that
+// races in while the scheduler shuts down) with codes.Unavailable, then frees the pinned buffers
+// and the device context.  No Schedule call is left blocked.
 func (g *GPUScheduler) Close() {
-	select {
-	case <-g.stop:
-	default:
+	g.closeOnce.Do(func() {
 		close(g.stop)
-	}
-	g.wg.Wait()
-	g.in.free()
-	g.out.free()
-	g.c.close()
+		g.wg.Wait() // batcher and refresher are gone: nobody reads g.queue any more
+		for {
+			select {
+			case w := <-g.queue:
+				w.done <- result{err: status.Error(codes.Unavailable, "gpu scheduler is shut down")}
+				continue
+			default:
+			}
+			break
+		}
+		g.in.free()
+		g.out.free()
+		g.c.close()
+	})
 }
 
 // Refresh re-packs the provider's current slice and uploads it as a new epoch.  One pack per
@@ -162,8 +173,19 @@ func (g *GPUScheduler) Schedule(req *scheduling.LLMRequest) (backend.Pod, error)
 	case <-g.stop:
 		return backend.Pod{}, status.Error(codes.Unavailable, "gpu scheduler is shut down")
 	}
-	r := <-w.done
-	return r.pod, r.err
+	// A request that slipped into the queue while Close was draining it is answered by the
+	// second arm: stop is closed for good, so no waiter can block forever.
+	select {
+	case r := <-w.done:
+		return r.pod, r.err
+	case <-g.stop:
+		select {
+		case r := <-w.done:
+			return r.pod, r.err
+		case <-time.After(g.opt.BatchWindow + 10*time.Millisecond):
+			return backend.Pod{}, status.Error(codes.Unavailable, "gpu scheduler is shut down")
+		}
+	}
 }
 
 func (g *GPUScheduler) batcher() {

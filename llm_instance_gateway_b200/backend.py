@@ -74,3 +74,60 @@ class InferenceModel:
 
 def IsCritical(model: InferenceModel) -> bool:          # backend/datastore.go:100-105
     return model.Spec.Criticality is not None and model.Spec.Criticality == CRITICAL
+
+
+class FakeDataStore:                         # backend/fake.go: FakeDataStore{Res map[string]*InferenceModel}
+    def __init__(self, Res: Optional[Dict[str, InferenceModel]] = None):
+        self.Res = dict(Res or {})
+
+    def FetchModelData(self, modelName: str) -> Optional[InferenceModel]:   # backend/datastore.go:70-76
+        return self.Res.get(modelName)
+
+
+_M64 = (1 << 64) - 1
+DRAW_DOMAIN = 0xA0761D6478BD642F            # LIG_DRAW_DOMAIN, include/lig.h
+
+
+class SplitMixSource:
+    """rand.Source64 over SplitMix64: the injected source the ABI defines the draw and the pick on."""
+
+    def __init__(self, state: int):
+        self.state = state & _M64
+
+    def Uint64(self) -> int:
+        self.state = (self.state + 0x9E3779B97F4A7C15) & _M64
+        z = self.state
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & _M64
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & _M64
+        return z ^ (z >> 31)
+
+    def Int63(self) -> int:
+        return self.Uint64() >> 1
+
+    def Int31(self) -> int:                  # math/rand: Int31() = Int63() >> 32
+        return self.Int63() >> 32
+
+    def Int31n(self, n: int) -> int:         # math/rand (Go 1.22) Rand.Int31n
+        if n <= 0:
+            raise ValueError("invalid argument to Int31n")      # Go panics
+        if n & (n - 1) == 0:
+            return self.Int31() & (n - 1)
+        mx = (1 << 31) - 1 - ((1 << 31) % n)
+        v = self.Int31()
+        while v > mx:
+            v = self.Int31()
+        return v % n
+
+
+def RandomWeightedDraw(model: InferenceModel, source: SplitMixSource) -> str:      # backend/datastore.go:78-98
+    """The reference seeds a fresh source per call (rand.NewSource(rand.Int63()), unseeded); here the
+    source is injected (include/lig.h: the request's private stream)."""
+    weights = 0
+    for tm in model.Spec.TargetModels:
+        weights += tm.Weight
+    randomVal = source.Int31n(weights)
+    for tm in model.Spec.TargetModels:
+        if randomVal < tm.Weight:
+            return tm.Name
+        randomVal -= tm.Weight
+    return ""
