@@ -284,6 +284,24 @@ int lig_schedule_models_batches_device(lig_ctx* ctx, uint64_t epoch, uint64_t se
 int lig_resolve_models(lig_ctx* ctx, uint64_t epoch, uint64_t seed, uint64_t first_index,
                        const uint32_t* model_ids, int R, lig_req* reqs_out, lig_mpick* out);
 
+/* ---- in-batch load feedback (opt-in; the default path never mutates the snapshot) ----------------
+ * The reference schedules every request against the scraped metrics as they are
+ * (scheduler.go:113-122 never writes them), so all requests of one class that arrive inside a
+ * 50 ms scrape window land on the same handful of survivors.  The simulator does account for
+ * load per pick (simulations/llm_ig_simulation/src/loadbalancer.py:608-625: the chosen pod's
+ * prefill queue grows immediately).  This entry point does the same at sub-batch granularity:
+ * the batch is cut into windows of `sub_batch` requests; after every window the number of picks
+ * each pod received — summed over all ranks with one ncclAllReduce(int32[P]) when the ctx has a
+ * communicator (lig_comm_init_rank) — is added to that pod's WaitingQueueSize in a PRIVATE copy of
+ * the snapshot, the class tables are rebuilt, and the next window is scheduled against them.
+ *   n_windows <= 0: ceil(R / sub_batch) windows; ranks of one communicator must pass the same
+ *   n_windows (trailing windows may be empty).  d_hist (nullable): int32[P], receives the total
+ *   picks per pod of this call (all ranks).  Resident epochs are not modified.  Enqueued on
+ *   `stream`, not synchronised.  Defined sequentially in oracle/feedback.py. */
+int lig_schedule_batch_feedback_device(lig_ctx* ctx, uint64_t epoch, uint64_t seed, const lig_req* d_reqs,
+                                       int R, lig_pick* d_out, int sub_batch, int n_windows,
+                                       int32_t* d_hist, void* stream);
+
 /* ---- several GPUs, one process (the reference runs ONE scheduler per process, main.go:137) ------
  * A lig_group owns one lig_ctx per listed CUDA device and an NCCL communicator over them
  * (ncclCommInitAll).  The request batch shards BY REQUEST (decisions are independent given a

@@ -124,6 +124,12 @@ struct lig_ctx {
   std::atomic<uint64_t> launches{0};
   void* comm = nullptr;                      // ncclComm_t, owned by lig_multi.cpp
 
+  // ---- load feedback (lig_schedule_batch_feedback_device): a private, mutable snapshot copy ----
+  std::mutex fb_mu;
+  Slot fb_scratch;                            // allocated at first use
+  int32_t* d_fb_hist = nullptr;               // picks per pod of the current window
+  cudaEvent_t fb_free = nullptr;              // the previous feedback call has finished with the scratch
+
   // ---- snapshots: two resident epochs ----
   Slot slot[2];
   uint64_t stamp = 0;
@@ -598,6 +604,8 @@ int max_batch_of(const lig_ctx* c) { return c->max_batch; }
 void*& comm_of(lig_ctx* c) { return c->comm; }
 static void (*g_comm_destructor)(void*) = nullptr;
 void set_comm_destructor(void (*fn)(void*)) { g_comm_destructor = fn; }
+static allreduce_fn g_allreduce = nullptr;
+void set_allreduce(allreduce_fn fn) { g_allreduce = fn; }
 
 int begin_write(lig_ctx* c, uint64_t epoch, int P, int A, cudaStream_t stream, bool own_stream,
                 SnapshotWrite* w) {
@@ -738,6 +746,48 @@ int lig_pack_snapshot(void* blob, int P, int A, const double* kv, const int32_t*
   return 0;
 }
 
+// HBM + pinned memory + events of one snapshot slot (the two resident epochs and, lazily, the
+// private scratch copy of the load-feedback mode).
+static int alloc_slot(lig_ctx* c, Slot& s) {
+  const Layout l = layout_for(c->max_pods, c->max_adapters);
+  const size_t n_classes = 2 * ((size_t)c->max_adapters + 1);
+  CUDA_TRY(cudaMalloc(&s.d_blob, l.total));
+  CUDA_TRY(cudaMalloc(&s.d_cls, n_classes * sizeof(ClassEntry)));
+  CUDA_TRY(cudaMalloc(&s.d_lists, list_pool_entries(n_classes, (size_t)c->max_pods) * sizeof(uint16_t)));
+  {
+    // the compact pool holds the two default lists plus up to 2 M more entries (4 MB); a
+    // snapshot whose lists do not fit keeps the strided tables only
+    size_t cap = list_pool_entries(n_classes, (size_t)c->max_pods);
+    const size_t bound = 2 * (size_t)c->max_pods + 16 + ((size_t)2 << 20);
+    if (cap > bound) cap = bound;
+    s.ctab_pool_capacity = (uint32_t)cap;
+    CUDA_TRY(cudaMalloc(&s.d_ctab, sizeof(CompactHeader) + n_classes * sizeof(ClassEntry) + cap * sizeof(uint16_t) + 16));
+    CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&s.h_hdr), sizeof(CompactHeader), cudaHostAllocDefault));
+    memset(s.h_hdr, 0, sizeof(CompactHeader));
+  }
+  CUDA_TRY(cudaHostAlloc(&s.h_blob, l.total, cudaHostAllocDefault));
+  CUDA_TRY(cudaEventCreateWithFlags(&s.ready, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreateWithFlags(&s.models_ready, cudaEventDisableTiming));
+  for (auto& ev : s.readers) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  return 0;
+}
+
+static void free_slot(Slot& s) {
+  cudaFree(s.d_blob);
+  cudaFree(s.d_cls);
+  cudaFree(s.d_lists);
+  cudaFree(s.d_ctab);
+  cudaFree(s.d_mtab);
+  if (s.h_mtab) cudaFreeHost(s.h_mtab);
+  if (s.models_ready) cudaEventDestroy(s.models_ready);
+  if (s.h_hdr) cudaFreeHost(s.h_hdr);
+  cudaFreeHost(s.h_blob);
+  if (s.ready) cudaEventDestroy(s.ready);
+  for (auto& ev : s.readers)
+    if (ev) cudaEventDestroy(ev);
+  s = Slot();
+}
+
 static int create_impl(lig_ctx* c, int device, int max_pods, int max_adapters, int max_batch) {
   CUDA_TRY(cudaSetDevice(device));
   c->device = device;
@@ -762,28 +812,8 @@ static int create_impl(lig_ctx* c, int device, int max_pods, int max_adapters, i
   if (need > c->smem_optin)
     return fail(LIG_ERR_INVALID, "max_pods=%d needs %zu B of per-CTA scratch, device allows %zu",
                 max_pods, need, c->smem_optin);
-  const Layout l = layout_for(max_pods, max_adapters);
-  const size_t n_classes = 2 * ((size_t)max_adapters + 1);
-  for (auto& s : c->slot) {
-    CUDA_TRY(cudaMalloc(&s.d_blob, l.total));
-    CUDA_TRY(cudaMalloc(&s.d_cls, n_classes * sizeof(ClassEntry)));
-    CUDA_TRY(cudaMalloc(&s.d_lists, list_pool_entries(n_classes, (size_t)max_pods) * sizeof(uint16_t)));
-    {
-      // the compact pool holds the two default lists plus up to 2 M more entries (4 MB); a
-      // snapshot whose lists do not fit keeps the strided tables only
-      size_t cap = list_pool_entries(n_classes, (size_t)max_pods);
-      const size_t bound = 2 * (size_t)max_pods + 16 + ((size_t)2 << 20);
-      if (cap > bound) cap = bound;
-      s.ctab_pool_capacity = (uint32_t)cap;
-      CUDA_TRY(cudaMalloc(&s.d_ctab, sizeof(CompactHeader) + n_classes * sizeof(ClassEntry) + cap * sizeof(uint16_t) + 16));
-      CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&s.h_hdr), sizeof(CompactHeader), cudaHostAllocDefault));
-      memset(s.h_hdr, 0, sizeof(CompactHeader));
-    }
-    CUDA_TRY(cudaHostAlloc(&s.h_blob, l.total, cudaHostAllocDefault));
-    CUDA_TRY(cudaEventCreateWithFlags(&s.ready, cudaEventDisableTiming));
-    CUDA_TRY(cudaEventCreateWithFlags(&s.models_ready, cudaEventDisableTiming));
-    for (auto& ev : s.readers) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-  }
+  for (auto& s : c->slot)
+    if (int rc = alloc_slot(c, s)) return rc;
   if (const char* e = getenv("LIG_PICK_PER_THREAD")) {
     int v2 = atoi(e);
     if (v2 == 1 || v2 == 2 || v2 == 4 || v2 == 8 || v2 == 16) c->pick_per_thread = v2;
@@ -912,20 +942,10 @@ void lig_destroy(lig_ctx* c) {
   lig_stream_close(c);   // a resident doorbell kernel would make the synchronize below wait forever
   cudaDeviceSynchronize();
   if (c->comm && ligi::g_comm_destructor) ligi::g_comm_destructor(c->comm);
-  for (auto& s : c->slot) {
-    cudaFree(s.d_blob);
-    cudaFree(s.d_cls);
-    cudaFree(s.d_lists);
-    cudaFree(s.d_ctab);
-    cudaFree(s.d_mtab);
-    if (s.h_mtab) cudaFreeHost(s.h_mtab);
-    if (s.models_ready) cudaEventDestroy(s.models_ready);
-    if (s.h_hdr) cudaFreeHost(s.h_hdr);
-    cudaFreeHost(s.h_blob);
-    if (s.ready) cudaEventDestroy(s.ready);
-    for (auto& ev : s.readers)
-      if (ev) cudaEventDestroy(ev);
-  }
+  for (auto& s : c->slot) free_slot(s);
+  if (c->fb_scratch.d_blob) free_slot(c->fb_scratch);
+  cudaFree(c->d_fb_hist);
+  if (c->fb_free) cudaEventDestroy(c->fb_free);
   if (c->mailbox) cudaFreeHost(c->mailbox);
   if (c->s_doorbell) cudaStreamDestroy(c->s_doorbell);
   for (int i = 0; i < lig_ctx::kItemSlots; ++i) {
@@ -1432,6 +1452,70 @@ int lig_pick_kernel_info(lig_ctx* c, uint64_t epoch, char* name, int name_len, i
   if (threads) *threads = t;
   if (table_bytes) *table_bytes = (int)s->h_hdr->bytes;
   if (tables_in_smem) *tables_in_smem = tab ? 1 : 0;
+  return 0;
+}
+
+int lig_schedule_batch_feedback_device(lig_ctx* c, uint64_t epoch, uint64_t seed, const lig_req* d_reqs,
+                                       int R, lig_pick* d_out, int sub_batch, int n_windows,
+                                       int32_t* d_hist, void* stream) {
+  if (!c || R < 0 || sub_batch < 1 || (R > 0 && (!d_reqs || !d_out)))
+    return fail(LIG_ERR_INVALID, "lig_schedule_batch_feedback_device: bad argument");
+  if (n_windows <= 0) n_windows = (R + sub_batch - 1) / sub_batch;
+  if ((long long)n_windows * sub_batch < R)
+    return fail(LIG_ERR_INVALID, "n_windows=%d x sub_batch=%d does not cover R=%d", n_windows, sub_batch, R);
+  std::lock_guard<std::mutex> fk(c->fb_mu);
+  CUDA_TRY(cudaSetDevice(c->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!c->fb_scratch.d_blob) {
+    if (c->stream_open) return fail(LIG_ERR_INVALID, "cannot allocate the feedback scratch while a doorbell stream is open");
+    if (int rc = alloc_slot(c, c->fb_scratch)) return rc;
+    CUDA_TRY(cudaMalloc(&c->d_fb_hist, (size_t)c->max_pods * sizeof(int32_t)));
+    CUDA_TRY(cudaEventCreateWithFlags(&c->fb_free, cudaEventDisableTiming));
+  }
+  Slot& fs = c->fb_scratch;
+  {
+    std::lock_guard<std::mutex> lk(c->mu);
+    Slot* s = nullptr;
+    if (int rc = resolve_slot(c, epoch, &s)) return rc;
+    CUDA_TRY(cudaStreamWaitEvent(st, c->fb_free, 0));       // an earlier feedback call on another stream
+    CUDA_TRY(cudaStreamWaitEvent(st, s->ready, 0));
+    fs.P = s->P;
+    fs.A = s->A;
+    fs.W = s->W;
+    CUDA_TRY(cudaMemcpyAsync(fs.d_blob, s->d_blob, layout_for(s->P, s->A).total, cudaMemcpyDeviceToDevice, st));
+    if (int rc = note_reader(*s, st)) return rc;
+  }
+  const int P = fs.P;
+  int* q = reinterpret_cast<int*>(fs.d_blob + layout_for(fs.P, fs.A).q);
+  if (P > 0) CUDA_TRY(cudaMemsetAsync(c->d_fb_hist, 0, (size_t)P * sizeof(int32_t), st));
+  if (d_hist && P > 0) CUDA_TRY(cudaMemsetAsync(d_hist, 0, (size_t)P * sizeof(int32_t), st));
+  for (int w = 0; w < n_windows; ++w) {
+    const long long lo = (long long)w * sub_batch;
+    const int n = lo >= R ? 0 : (int)((R - lo) < sub_batch ? (R - lo) : sub_batch);
+    {
+      std::lock_guard<std::mutex> lk(c->mu);                 // launch counters, item ring
+      if (int rc = launch_class_build(c, fs, st)) return rc;
+      if (n > 0) {
+        // the tables of the scratch copy change every window: always the strided tables through
+        // L1 (no host round trip for the compact header inside the loop)
+        if (int rc = launch_pick(c, fs, seed, d_reqs + lo, n, d_out + lo, st)) return rc;
+      }
+    }
+    if (n > 0 && P > 0) {
+      lig_pick_hist_kernel<<<(n + 255) / 256 < 2048 ? (n + 255) / 256 : 2048, 256, 0, st>>>(
+          reinterpret_cast<const int2*>(d_out + lo), n, c->d_fb_hist);
+      CUDA_TRY(cudaGetLastError());
+      c->launches++;
+    }
+    if (P > 0) {
+      if (c->comm && ligi::g_allreduce)                      // picks of this window on every rank
+        if (int rc = ligi::g_allreduce(c, c->d_fb_hist, P, st)) return rc;
+      lig_apply_feedback_kernel<<<(P + 255) / 256, 256, 0, st>>>(q, c->d_fb_hist, d_hist, P);
+      CUDA_TRY(cudaGetLastError());
+      c->launches++;
+    }
+  }
+  CUDA_TRY(cudaEventRecord(c->fb_free, st));
   return 0;
 }
 

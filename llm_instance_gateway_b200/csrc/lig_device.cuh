@@ -1571,6 +1571,27 @@ lig_pick_models_stream_kernel(const uint32_t* __restrict__ ids, uint32_t* __rest
   }
 }
 
+// ---- K2f: load feedback between the windows of a batch (opt-in) -----------------------------------
+// hist[pod] += 1 for every pick of the window that chose a pod.
+__global__ void lig_pick_hist_kernel(const int2* __restrict__ picks, int n, int* __restrict__ hist) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int pod = picks[i].x;
+    if (pod >= 0) atomicAdd(hist + pod, 1);
+  }
+}
+// WaitingQueueSize += picks of the window (all ranks); total += window; window = 0.
+__global__ void lig_apply_feedback_kernel(int* __restrict__ q, int* __restrict__ hist_window,
+                                          int* __restrict__ hist_total, int P) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const int h = hist_window[p];
+  // saturating: a queue size beyond int32 is not representable in the device record
+  const long long nq = (long long)q[p] + h;
+  q[p] = nq > 0x7fffffffLL ? 0x7fffffff : (int)nq;
+  if (hist_total) hist_total[p] += h;
+  hist_window[p] = 0;
+}
+
 // ---- K3: persistent doorbell kernel (streaming micro-batches) ------------------------------------
 // One resident CTA polls a mailbox in page-locked host memory.  The host writes the micro-batch
 // (header + descriptors), then the ticket; the CTA schedules it with the same pick_one() and

@@ -45,5 +45,9 @@ int max_batch_of(const lig_ctx* c);
 // lig_destroy).
 void*& comm_of(lig_ctx* c);
 void set_comm_destructor(void (*fn)(void*));
+// In-place int32 sum over the ranks of the ctx's communicator (set by lig_multi.cpp once NCCL is
+// loaded); lig.cu calls it between the windows of the load-feedback mode.
+typedef int (*allreduce_fn)(lig_ctx* c, int32_t* d_values, int n, cudaStream_t stream);
+void set_allreduce(allreduce_fn fn);
 
 }  // namespace ligi

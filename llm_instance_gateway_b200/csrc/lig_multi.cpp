@@ -84,10 +84,19 @@ void destroy_comm(void* p) {
 
 CommState* comm_state(lig_ctx* c) { return static_cast<CommState*>(ligi::comm_of(c)); }
 
+int allreduce_i32(lig_ctx* c, int32_t* d_values, int n, cudaStream_t stream) {
+  CommState* cs = comm_state(c);
+  if (!cs || cs->n_ranks <= 1 || n == 0) return 0;
+  ncclResult_t r = g_nccl.AllReduce(d_values, d_values, (size_t)n, ncclInt32, ncclSum, cs->comm, stream);
+  if (r != ncclSuccess) return fail(LIG_ERR_NCCL, "ncclAllReduce failed: %s", g_nccl.GetErrorString(r));
+  return 0;
+}
+
 int need_nccl() {
   std::call_once(g_nccl_once, [] {
     load_nccl();
     ligi::set_comm_destructor(&destroy_comm);
+    ligi::set_allreduce(&allreduce_i32);
   });
   if (!g_nccl.ok) return fail(LIG_ERR_NCCL, "NCCL is not available: %s", g_nccl_why);
   return 0;

@@ -114,6 +114,13 @@ class Engine:
                                              _ptr(reqs), _ptr(out)))
         return reqs, out
 
+    def schedule_batch_feedback_device(self, epoch: int, seed: int, d_reqs: int, R: int, d_out: int, sub_batch: int,
+                                       n_windows: int = 0, d_hist: int = 0, stream: int = 0) -> None:
+        """Opt-in in-batch load feedback: windows of `sub_batch` requests, the picks of each window
+        (all ranks) are added to the pods' queue sizes before the next window is scheduled."""
+        N.check(self._lib.lig_schedule_batch_feedback_device(self._ctx, epoch, seed, d_reqs, R, d_out, sub_batch,
+                                                             n_windows, d_hist or None, stream or None))
+
     def pick_kernel_info(self, epoch: int) -> dict:
         name = C.create_string_buffer(64)
         grid, threads, tb, in_smem = C.c_int(), C.c_int(), C.c_int(), C.c_int()

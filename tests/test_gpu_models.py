@@ -138,6 +138,5 @@ def test_model_table_validation_and_edge_tables(oracle):
         with pytest.raises(N.LigError) as ei:
             e.upload_models(1, bad)
         assert ei.value.code == N.LIG_ERR_RANGE
-        # the refused upload left the epoch without a model table
-        with pytest.raises(N.LigError):
-            e.schedule_models_batch(1, 3, ids)
+        # a refused upload changes nothing: the previous table keeps serving
+        assert np.array_equal(e.schedule_models_batch(1, 3, ids), want)

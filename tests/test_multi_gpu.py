@@ -114,6 +114,17 @@ def _comm_worker(rank, world, id_path, out_dir):
     eng.comm_allreduce_i32(hist.data_ptr(), P, 0)
     torch.cuda.synchronize()
     assert int(hist[0]) == world * (world + 1) // 2
+    # load feedback across ranks: every window's picks are all-reduced inside the library
+    S_FB = 8192
+    n_windows = max((R * (r + 1) // world - R * r // world + S_FB - 1) // S_FB for r in range(world))
+    d_fb = torch.zeros((hi - lo) * 8, dtype=torch.uint8, device="cuda")
+    d_hist = torch.zeros(P, dtype=torch.int32, device="cuda")
+    with torch.cuda.stream(stream):
+        eng.schedule_batch_feedback_device(5, SEED, d_reqs.data_ptr(), hi - lo, d_fb.data_ptr(), S_FB, n_windows,
+                                           d_hist.data_ptr(), stream.cuda_stream)
+    stream.synchronize()
+    np.save(os.path.join(out_dir, f"fb_{rank}.npy"), d_fb.cpu().numpy().view(PICK_DTYPE))
+    np.save(os.path.join(out_dir, f"fbhist_{rank}.npy"), d_hist.cpu().numpy())
     np.save(os.path.join(out_dir, f"picks5_{rank}.npy"), got)
     np.save(os.path.join(out_dir, f"picks6_{rank}.npy"), d_out.cpu().numpy().view(PICK_DTYPE))
     eng.close()
@@ -129,6 +140,17 @@ def test_comm_one_process_per_gpu_matches_oracle(tmp_path, oracle):
         snap = WL.make_snapshot(P, A, seed=snap_seed)
         got = np.concatenate([np.load(os.path.join(str(tmp_path), f"picks{epoch}_{r}.npy")) for r in range(world)])
         assert np.array_equal(got, _oracle_whole_batch(oracle, snap, reqs, seed)), epoch
+    # the feedback mode over the ranks == its sequential definition with the same shards
+    from oracle import feedback as FB
+    snap = WL.make_snapshot(P, A, seed=61)
+    pk = snap.packed
+    shards = [(R * r // world, R * (r + 1) // world) for r in range(world)]
+    want, want_total, _ = FB.schedule_batch_feedback(pk.P, pk.A, pk.kv, snap.q64, pk.n_active, pk.max_active, pk.bitmap,
+                                                     reqs, SEED, 8192, shards)
+    got = np.concatenate([np.load(os.path.join(str(tmp_path), f"fb_{r}.npy")) for r in range(world)])
+    assert np.array_equal(got, want)
+    for r in range(world):
+        assert np.array_equal(np.load(os.path.join(str(tmp_path), f"fbhist_{r}.npy")).astype(np.int64), want_total), r
 
 
 def test_group_of_one_needs_no_nccl(oracle):
