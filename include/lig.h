@@ -138,6 +138,20 @@ int lig_upload_snapshot(lig_ctx* ctx, uint64_t epoch, int P, int A, const double
                         const int32_t* q, const uint16_t* n_active, const uint16_t* max_active,
                         const uint32_t* bitmap_adapter_major);
 
+/* Delta form of lig_upload_snapshot for the refresh tick (backend/provider.go:134-179 re-scrapes
+ * every pod, but between two ticks most pods report the same metrics): `new_epoch` becomes
+ * `base_epoch` (which must be resident and stays so, untouched) with n_dirty pods replaced.  P
+ * and A are those of the base.  For dirty pod i: pod_idx[i], its four column values, and its
+ * COMPLETE ActiveModels as adapter ids adapter_ids[adapter_offsets[i] .. adapter_offsets[i+1]).
+ * Only the delta crosses PCIe; the base blob is copied device-to-device, the dirty rows and
+ * bitmap bits are patched by a kernel, and the class tables are rebuilt.  LIG_ERR_INVALID when
+ * the base epoch is the slot the new epoch would have to overwrite (it is the older of the two
+ * resident epochs): fall back to lig_upload_snapshot. */
+int lig_update_snapshot(lig_ctx* ctx, uint64_t new_epoch, uint64_t base_epoch, int n_dirty,
+                        const int32_t* pod_idx, const double* kv, const int32_t* q,
+                        const uint16_t* n_active, const uint16_t* max_active,
+                        const int32_t* adapter_offsets, const int32_t* adapter_ids);
+
 /* Same, but the packed blob is already in HBM (e.g. the receive buffer of an NCCL broadcast of
  * the snapshot).  The blob is copied into the ctx on `stream` (a cudaStream_t, may be NULL =
  * legacy default stream); table build is enqueued on the same stream, nothing is synchronised. */

@@ -34,7 +34,7 @@ EXPORTED_SYMBOLS = (
     "lig_comm_unique_id", "lig_comm_init_rank", "lig_comm_upload_snapshot_device", "lig_comm_upload_snapshot",
     "lig_comm_allreduce_i32",
     "lig_upload_models", "lig_schedule_models_batch", "lig_schedule_models_batches_device", "lig_resolve_models",
-    "lig_pick_kernel_info", "lig_schedule_batch_feedback_device",
+    "lig_pick_kernel_info", "lig_schedule_batch_feedback_device", "lig_update_snapshot",
 )
 
 
@@ -122,6 +122,7 @@ def load() -> C.CDLL:
     lib.lig_schedule_models_batches_device.argtypes = [vp, u64, u64, u64, vp, i32, vp, i32, vp]
     lib.lig_resolve_models.argtypes = [vp, u64, u64, u64, vp, i32, vp, vp]
     lib.lig_schedule_batch_feedback_device.argtypes = [vp, u64, u64, vp, i32, vp, i32, i32, vp, vp]
+    lib.lig_update_snapshot.argtypes = [vp, u64, u64, i32, vp, vp, vp, vp, vp, vp, vp]
     lib.lig_pick_kernel_info.argtypes = [vp, u64, C.c_char_p, i32, C.POINTER(i32), C.POINTER(i32),
                                          C.POINTER(i32), C.POINTER(i32)]
     for name in EXPORTED_SYMBOLS:

@@ -131,3 +131,81 @@ def RandomWeightedDraw(model: InferenceModel, source: SplitMixSource) -> str:   
             return tm.Name
         randomVal -= tm.Weight
     return ""
+
+
+# ---- backend/vllm/metrics.go:73-166: scraped metric families -> PodMetrics -------------------------
+LoraRequestInfoMetricName = "vllm:lora_requests_info"
+LoraRequestInfoRunningAdaptersMetricName = "running_lora_adapters"
+LoraRequestInfoMaxAdaptersMetricName = "max_lora"
+RunningQueueSizeMetricName = "vllm:num_requests_running"
+WaitingQueueSizeMetricName = "vllm:num_requests_waiting"
+KVCacheUsagePercentMetricName = "vllm:gpu_cache_usage_perc"
+
+
+def _go_atoi(s: str) -> int:
+    """strconv.Atoi: optional sign, decimal digits only (no spaces, no underscores)."""
+    body = s[1:] if s[:1] in "+-" else s
+    if not body or not all("0" <= ch <= "9" for ch in body):
+        raise ValueError(f'strconv.Atoi: parsing "{s}": invalid syntax')
+    return int(s)
+
+
+def getLatestMetric(metricFamilies: Dict[str, list], metricName: str):        # metrics.go:151-171
+    """A metric family is a list of dicts {"value": float, "timestamp_ms": int, "labels": {...}}.
+    vLLM sets no timestamps, so ">=" makes this the LAST series of the family."""
+    mf = metricFamilies.get(metricName)
+    if mf is None:
+        raise KeyError(f'metric family "{metricName}" not found')
+    if len(mf) == 0:
+        raise KeyError(f'no metrics available for "{metricName}"')
+    latestTs, latest = 0, None
+    for m in mf:
+        if m.get("timestamp_ms", 0) >= latestTs:
+            latestTs, latest = m.get("timestamp_ms", 0), m
+    return latest
+
+
+def getLatestLoraMetric(metricFamilies: Dict[str, list]):                     # metrics.go:131-148
+    """The series with the largest VALUE (the value is the series' creation timestamp)."""
+    mf = metricFamilies.get(LoraRequestInfoMetricName)
+    if mf is None:
+        raise KeyError(f'metric family "{LoraRequestInfoMetricName}" not found')
+    latestTs, latest = 0.0, None
+    for m in mf:
+        if m.get("value", 0.0) > latestTs:
+            latestTs, latest = m.get("value", 0.0), m
+    return latest
+
+
+def promToPodMetrics(metricFamilies: Dict[str, list], existing: PodMetrics):   # metrics.go:73-129
+    """Returns (updated PodMetrics, list of error strings).  Starts from existing.Clone(), which
+    does NOT carry MaxActiveModels over (backend/types.go:37-53): a scrape without a parsable
+    max_lora label leaves MaxActiveModels at 0 — the quirk the scheduler then sees."""
+    errs: List[str] = []
+    updated = existing.Clone()
+    for name, field_, conv in ((RunningQueueSizeMetricName, "RunningQueueSize", int),
+                               (WaitingQueueSizeMetricName, "WaitingQueueSize", int),
+                               (KVCacheUsagePercentMetricName, "KVCacheUsagePercent", float)):
+        try:
+            m = getLatestMetric(metricFamilies, name)
+            setattr(updated.Metrics, field_, conv(m["value"]))       # int(float64): truncation toward zero
+        except KeyError as ex:
+            errs.append(str(ex.args[0]))
+    lora = None
+    try:
+        lora = getLatestLoraMetric(metricFamilies)
+    except KeyError as ex:
+        errs.append(str(ex.args[0]))
+    if lora is not None:
+        updated.Metrics.ActiveModels = {}
+        for lname, lvalue in lora.get("labels", {}).items():
+            if lname == LoraRequestInfoRunningAdaptersMetricName and lvalue != "":
+                for adapter in lvalue.split(","):
+                    updated.Metrics.ActiveModels[adapter] = 0
+            if lname == LoraRequestInfoMaxAdaptersMetricName and lvalue != "":
+                try:
+                    updated.Metrics.MaxActiveModels = _go_atoi(lvalue)
+                except ValueError as ex:
+                    updated.Metrics.MaxActiveModels = 0              # strconv.Atoi returns 0 with the error
+                    errs.append(str(ex))
+    return updated, errs

@@ -39,10 +39,19 @@ Status NewScheduler(std::shared_ptr<PodMetricsProvider> pmp, const Options& opt,
   std::unique_ptr<Scheduler> s(new Scheduler());
   s->pmp_ = std::move(pmp);
   s->opt_ = opt;
-  if (lig_create(&s->ctx_, opt.device, opt.max_pods, opt.max_adapters, opt.max_batch) != 0)
-    return LigFailure("lig_create");
   lig_thresholds t{opt.kv_cache_threshold, opt.queue_threshold_critical, opt.queueing_threshold_lora};
-  if (lig_set_thresholds(s->ctx_, &t) != 0) return LigFailure("lig_set_thresholds");
+  if (opt.devices.size() > 1) {
+    if (opt.use_doorbell) return Errorf(Internal, "the doorbell stream is a single-device mode");
+    if (lig_group_create(&s->group_, opt.devices.data(), (int)opt.devices.size(), opt.max_pods, opt.max_adapters,
+                         opt.max_batch) != 0)
+      return LigFailure("lig_group_create");
+    if (lig_group_set_thresholds(s->group_, &t) != 0) return LigFailure("lig_group_set_thresholds");
+  } else {
+    const int dev = opt.devices.size() == 1 ? opt.devices[0] : opt.device;
+    if (lig_create(&s->ctx_, dev, opt.max_pods, opt.max_adapters, opt.max_batch) != 0)
+      return LigFailure("lig_create");
+    if (lig_set_thresholds(s->ctx_, &t) != 0) return LigFailure("lig_set_thresholds");
+  }
   s->h_reqs_ = static_cast<lig_req*>(lig_host_alloc((size_t)opt.max_batch * sizeof(lig_req)));
   s->h_picks_ = static_cast<lig_pick*>(lig_host_alloc((size_t)opt.max_batch * sizeof(lig_pick)));
   if (!s->h_reqs_ || !s->h_picks_) return LigFailure("lig_host_alloc");
@@ -75,6 +84,7 @@ Scheduler::~Scheduler() {
   if (h_reqs_) lig_host_free(h_reqs_);
   if (h_picks_) lig_host_free(h_picks_);
   if (ctx_) lig_destroy(ctx_);
+  if (group_) lig_group_destroy(group_);
 }
 
 // One pack per refresh tick replaces the per-request AllPodMetrics() of scheduler.go:114-115.
@@ -123,8 +133,10 @@ Status Scheduler::RefreshImpl() {
   std::vector<int64_t> q(P), na(P), ma(P);
   if (!intern_) intern_ = std::make_shared<InternTable>();
   bool table_changed = false;
+  std::vector<char> memo_dirty;
   for (int attempt = 0; attempt < 2; ++attempt) {
     memo_.resize((size_t)P);
+    memo_dirty.assign((size_t)P, 0);
     snap->pods.clear();
     for (int p = 0; p < P; ++p) {
       const backend::PodMetrics& pm = *pods[p];
@@ -141,6 +153,7 @@ Status Scheduler::RefreshImpl() {
           if (m.names[k++] != kvp.first) { same = false; break; }
       }
       if (same) continue;
+      memo_dirty[(size_t)p] = 1;
       m.names.clear();
       m.ids.clear();
       for (const auto& kvp : pm.metrics.ActiveModels) {
@@ -174,9 +187,46 @@ Status Scheduler::RefreshImpl() {
     return LigFailure("lig_pack_pods");
   snap->epoch = next_epoch_++;
   const auto t_packed = std::chrono::steady_clock::now();
-  if (lig_upload_snapshot(ctx_, snap->epoch, P, A, kv.data(), q32.data(), na16.data(), ma16.data(),
-                          bitmap.data()) != 0)
-    return LigFailure("lig_upload_snapshot");
+  // Which pods changed since the last uploaded tick?  With the adapter table and the pool size
+  // unchanged and few dirty pods, only the delta crosses PCIe (lig_update_snapshot); the base is
+  // the previous epoch, still resident in the other slot.
+  std::vector<int32_t> dirty;
+  const bool comparable = !group_ && prev_epoch_ != 0 && !table_changed && prev_A_ == A && (int)prev_q_.size() == P;
+  if (comparable) {
+    for (int p = 0; p < P; ++p)
+      if (memo_dirty[(size_t)p] || prev_q_[(size_t)p] != q32[(size_t)p] || prev_na_[(size_t)p] != na16[(size_t)p] ||
+          prev_ma_[(size_t)p] != ma16[(size_t)p] || memcmp(&prev_kv_[(size_t)p], &kv[(size_t)p], sizeof(double)) != 0)
+        dirty.push_back(p);
+  }
+  bool used_delta = false;
+  if (comparable && (int)dirty.size() * 4 <= P) {
+    std::vector<double> dkv(dirty.size());
+    std::vector<int32_t> dq(dirty.size()), doff(dirty.size() + 1, 0), dids;
+    std::vector<uint16_t> dna(dirty.size()), dma(dirty.size());
+    for (size_t i = 0; i < dirty.size(); ++i) {
+      const size_t p = (size_t)dirty[i];
+      dkv[i] = kv[p]; dq[i] = q32[p]; dna[i] = na16[p]; dma[i] = ma16[p];
+      dids.insert(dids.end(), memo_[p].ids.begin(), memo_[p].ids.end());
+      doff[i + 1] = (int32_t)dids.size();
+    }
+    const int rc = lig_update_snapshot(ctx_, snap->epoch, prev_epoch_, (int)dirty.size(), dirty.data(), dkv.data(),
+                                       dq.data(), dna.data(), dma.data(), doff.data(), dids.data());
+    if (rc == 0) used_delta = true;
+    else if (rc != LIG_ERR_INVALID && rc != LIG_ERR_STALE_EPOCH) return LigFailure("lig_update_snapshot");
+  }
+  if (!used_delta) {
+    const int rc = group_ ? lig_group_upload_snapshot(group_, snap->epoch, P, A, kv.data(), q32.data(), na16.data(),
+                                                      ma16.data(), bitmap.data())
+                          : lig_upload_snapshot(ctx_, snap->epoch, P, A, kv.data(), q32.data(), na16.data(),
+                                                ma16.data(), bitmap.data());
+    if (rc != 0) return LigFailure(group_ ? "lig_group_upload_snapshot" : "lig_upload_snapshot");
+  }
+  prev_kv_ = kv;
+  prev_q_ = q32;
+  prev_na_ = na16;
+  prev_ma_ = ma16;
+  prev_A_ = A;
+  prev_epoch_ = snap->epoch;
   {
     std::lock_guard<std::mutex> lk(snap_mu_);
     snap_ = std::move(snap);
@@ -184,6 +234,8 @@ Status Scheduler::RefreshImpl() {
   const auto t_done = std::chrono::steady_clock::now();
   std::lock_guard<std::mutex> sk(stats_mu_);
   stats_.refreshes++;
+  stats_.delta_refreshes += used_delta ? 1 : 0;
+  stats_.last_dirty_pods = comparable ? dirty.size() : (uint64_t)P;
   stats_.excluded_pods = excluded;
   stats_.last_pack_us = std::chrono::duration<double, std::micro>(t_packed - t_begin).count();
   stats_.last_upload_us = std::chrono::duration<double, std::micro>(t_done - t_packed).count();
@@ -293,7 +345,8 @@ void Scheduler::Flush(std::vector<Waiter*>& batch) {
         h_reqs_[i].flags = r.Critical ? LIG_REQ_CRITICAL : 0u;
         h_reqs_[i].rand_key = splitmix_next(rng_state_);
       }
-      rc = (opt_.use_doorbell && n <= lig_stream_capacity())
+      rc = group_ ? lig_group_schedule_batch(group_, snap->epoch, seed_, h_reqs_, n, h_picks_)
+           : (opt_.use_doorbell && n <= lig_stream_capacity())
                ? lig_stream_submit(ctx_, snap->epoch, seed_, h_reqs_, n, h_picks_)
                : lig_schedule_batch(ctx_, snap->epoch, seed_, h_reqs_, n, h_picks_);
       if (rc != LIG_ERR_STALE_EPOCH) break;   // two refreshes raced past this batch: re-resolve
@@ -332,10 +385,61 @@ void Scheduler::Flush(std::vector<Waiter*>& batch) {
   }
 }
 
+Status Scheduler::ScheduleModel(backend::ModelDataStore& datastore, const std::string& model,
+                                std::string* resolvedTargetModel, backend::Pod* targetPod) {
+  auto modelObj = datastore.FetchModelData(model);                              // request.go:42-45
+  if (!modelObj) return Errorf(Unknown, "error finding a model object in InferenceModel for input " + model);
+  std::string modelName = model;
+  if (!modelObj->TargetModels.empty()) {                                        // request.go:46-51
+    const uint64_t key = model_draws_.fetch_add(1, std::memory_order_relaxed) + 1;
+    modelName = backend::RandomWeightedDraw(*modelObj, backend::SplitMixSource{seed_ ^ key ^ LIG_DRAW_DOMAIN});
+    if (modelName.empty()) return Errorf(Unknown, "error getting target model name for model " + modelObj->ModelName);
+  }
+  LLMRequest req;                                                               // request.go:52-56
+  req.Model = model;
+  req.ResolvedTargetModel = modelName;
+  req.Critical = modelObj->Critical;
+  Status st = Schedule(req, targetPod);
+  if (!st.ok()) st.message = "failed to find target pod: " + st.message;        // request.go:73-75 (%w keeps the code)
+  if (resolvedTargetModel) *resolvedTargetModel = modelName;
+  return st;
+}
+
 Stats Scheduler::stats() const {
   std::lock_guard<std::mutex> sk(stats_mu_);
   return stats_;
 }
 
 }  // namespace scheduling
+
+namespace backend {
+
+uint64_t SplitMixSource::Uint64() {
+  uint64_t z = (state += 0x9E3779B97F4A7C15ull);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+int32_t SplitMixSource::Int31n(int32_t n) {            // math/rand (Go 1.22) Rand.Int31n; n > 0
+  if ((n & (n - 1)) == 0) return Int31() & (n - 1);
+  const int32_t mx = (int32_t)((1u << 31) - 1 - (uint32_t)((1ull << 31) % (uint64_t)n));
+  int32_t v = Int31();
+  while (v > mx) v = Int31();
+  return v % n;
+}
+
+std::string RandomWeightedDraw(const InferenceModel& model, SplitMixSource source) {   // datastore.go:78-98
+  int32_t weights = 0;
+  for (const TargetModel& tm : model.TargetModels) weights = (int32_t)((uint32_t)weights + (uint32_t)tm.Weight);
+  if (weights <= 0) return "";                          // Go's Int31n panics here
+  int32_t randomVal = source.Int31n(weights);
+  for (const TargetModel& tm : model.TargetModels) {
+    if (randomVal < tm.Weight) return tm.Name;
+    randomVal -= tm.Weight;
+  }
+  return "";
+}
+
+}  // namespace backend
 }  // namespace lig

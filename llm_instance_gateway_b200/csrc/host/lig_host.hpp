@@ -28,6 +28,7 @@
 #include <vector>
 
 struct lig_ctx;
+struct lig_group;
 struct lig_req;
 struct lig_pick;
 
@@ -54,6 +55,36 @@ struct PodMetrics {                  // backend/types.go:28-31
   Pod pod;
   Metrics metrics;
 };
+
+// api/v1alpha1/inferencemodel_types.go: the fields the request path reads
+struct TargetModel {
+  std::string Name;
+  int32_t Weight = 0;
+};
+struct InferenceModel {
+  std::string ModelName;             // Spec.ModelName: the key requests carry in "model"
+  bool Critical = false;             // Spec.Criticality != nil && *Spec.Criticality == Critical
+  std::vector<TargetModel> TargetModels;
+};
+
+class ModelDataStore {               // handlers/server.go:47-49
+ public:
+  virtual ~ModelDataStore() = default;
+  virtual std::shared_ptr<const InferenceModel> FetchModelData(const std::string& modelName) = 0;
+};
+
+// A rand.Source over SplitMix64: the injected source include/lig.h defines the draw and the pick on.
+struct SplitMixSource {
+  uint64_t state;
+  uint64_t Uint64();
+  int32_t Int31() { return (int32_t)(Uint64() >> 33); }          // Int63() >> 32
+  int32_t Int31n(int32_t n);                                      // math/rand (Go 1.22)
+};
+
+// RandomWeightedDraw(model, seed)                                 backend/datastore.go:78-98
+// Returns "" like the reference when no target is hit; weights summing to <= 0 (where Go's
+// Int31n panics) also return "".
+std::string RandomWeightedDraw(const InferenceModel& model, SplitMixSource source);
 
 }  // namespace backend
 
@@ -83,6 +114,9 @@ class PodMetricsProvider {           // scheduling/scheduler.go:108-110
 
 struct Options {
   int device = 0;
+  // More than one entry: ONE scheduler owns all listed GPUs (lig_group_*): the snapshot is
+  // replicated by an in-library ncclBroadcast per refresh, every flushed batch is sharded by request.
+  std::vector<int> devices;
   int max_pods = 4096;
   int max_adapters = 1024;
   int max_batch = 1 << 16;
@@ -110,6 +144,8 @@ struct Stats {
   uint64_t max_batch = 0;      // largest batch flushed
   uint64_t refreshes = 0;      // snapshots uploaded
   uint64_t stale_retries = 0;  // batches re-resolved after LIG_ERR_STALE_EPOCH
+  uint64_t delta_refreshes = 0;    // refreshes that went through lig_update_snapshot (dirty pods only)
+  uint64_t last_dirty_pods = 0;    // pods whose metrics changed at the last refresh
   uint64_t failed_refreshes = 0;   // Refresh() calls that kept the previous snapshot (see last_refresh_error)
   uint64_t excluded_pods = 0;      // pods left out of the last snapshot: a metric did not fit the device record
   double last_pack_us = 0;     // last Refresh: provider slice -> columns + bitmap (host)
@@ -128,6 +164,14 @@ class Scheduler {
   // handlers/server.go:97-109); Unknown for the "resulted 0 pods" case; Internal for a
   // batch-level (CUDA) failure.                                       scheduler.go:113-122
   Status Schedule(const LLMRequest& req, backend::Pod* targetPod);
+
+  // The resolve step of HandleRequestBody (handlers/request.go:42-56) followed by Schedule:
+  // FetchModelData, RandomWeightedDraw when TargetModels is non-empty, IsCritical.  Fills
+  // *resolvedTargetModel (the body's "model" is rewritten with it, request.go:60-69).  Errors as the
+  // reference: Unknown "error finding a model object in InferenceModel for input <model>" /
+  // "error getting target model name for model <name>".
+  Status ScheduleModel(backend::ModelDataStore& datastore, const std::string& model, std::string* resolvedTargetModel,
+                       backend::Pod* targetPod);
 
   // Re-read the provider and upload a new snapshot epoch (call on every metrics refresh).
   Status Refresh();
@@ -157,6 +201,13 @@ class Scheduler {
     std::vector<std::string> names;
     std::vector<int> ids;
   };
+  // last uploaded columns, to find the dirty pods of a tick (delta upload)
+  std::vector<double> prev_kv_;
+  std::vector<int32_t> prev_q_;
+  std::vector<uint16_t> prev_na_, prev_ma_;
+  int prev_A_ = -1;
+  uint64_t prev_epoch_ = 0;
+  std::atomic<uint64_t> model_draws_{0};
   std::shared_ptr<InternTable> intern_;
   std::vector<PodMemo> memo_;
   // Lives on the caller's stack.  `done` goes 0 -> 1 (result published, the caller may read it)
@@ -175,6 +226,7 @@ class Scheduler {
   std::shared_ptr<PodMetricsProvider> pmp_;
   Options opt_;
   lig_ctx* ctx_ = nullptr;
+  lig_group* group_ = nullptr;     // set instead of ctx_ when Options::devices lists several GPUs
   lig_req* h_reqs_ = nullptr;      // pinned, device-mapped (lig_host_alloc)
   lig_pick* h_picks_ = nullptr;
   uint64_t seed_ = 0;

@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <thread>
 
 #include "lig_host.hpp"
@@ -23,6 +24,16 @@ struct ligh_provider : public scheduling::PodMetricsProvider {
 struct ligh_scheduler {
   std::shared_ptr<ligh_provider> provider;
   std::unique_ptr<Scheduler> sched;
+};
+
+struct ligh_datastore : public backend::ModelDataStore {     // backend/fake.go: FakeDataStore
+  std::mutex mu;
+  std::map<std::string, std::shared_ptr<const backend::InferenceModel>> res;
+  std::shared_ptr<const backend::InferenceModel> FetchModelData(const std::string& name) override {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = res.find(name);
+    return it == res.end() ? nullptr : it->second;
+  }
 };
 
 namespace {
@@ -92,6 +103,59 @@ ligh_scheduler* ligh_scheduler_new2(ligh_provider* p, int device, int max_pods, 
   return s;
 }
 
+ligh_scheduler* ligh_scheduler_new_devices(ligh_provider* p, const int* devices, int n_devices, int max_pods,
+                                           int max_adapters, int max_batch, int flush_size, int window_us,
+                                           int refresh_ms, uint64_t seed, char* err, int err_cap) {
+  scheduling::Options o;
+  o.devices.assign(devices, devices + n_devices);
+  o.max_pods = max_pods;
+  o.max_adapters = max_adapters;
+  o.max_batch = max_batch;
+  o.flush_size = flush_size;
+  o.batch_window = std::chrono::microseconds(window_us);
+  o.refresh_interval = std::chrono::milliseconds(refresh_ms);
+  o.seed = seed;
+  auto* s = new ligh_scheduler();
+  s->provider = share(p);
+  scheduling::Status st = scheduling::NewScheduler(s->provider, o, &s->sched);
+  if (!st.ok()) {
+    put(err, err_cap, st.message);
+    delete s;
+    return nullptr;
+  }
+  return s;
+}
+
+ligh_datastore* ligh_datastore_new(void) { return new ligh_datastore(); }
+void ligh_datastore_free(ligh_datastore* d) { delete d; }
+
+int ligh_datastore_set_model(ligh_datastore* d, const char* model_name, int critical, int n_targets,
+                             const char* const* target_names, const int32_t* weights) {
+  if (!d || !model_name || n_targets < 0) return -1;
+  auto m = std::make_shared<backend::InferenceModel>();
+  m->ModelName = model_name;
+  m->Critical = critical != 0;
+  for (int k = 0; k < n_targets; ++k) m->TargetModels.push_back(backend::TargetModel{target_names[k], weights[k]});
+  std::lock_guard<std::mutex> lk(d->mu);
+  d->res[model_name] = std::move(m);
+  return 0;
+}
+
+int ligh_schedule_model(ligh_scheduler* s, ligh_datastore* d, const char* model, char* resolved, int resolved_cap,
+                        char* name, int name_cap, char* addr, int addr_cap, char* err, int err_cap) {
+  backend::Pod pod;
+  std::string target;
+  scheduling::Status st = s->sched->ScheduleModel(*d, model ? model : "", &target, &pod);
+  put(resolved, resolved_cap, target);
+  if (st.ok()) {
+    put(name, name_cap, pod.Name);
+    put(addr, addr_cap, pod.Address);
+  } else {
+    put(err, err_cap, st.message);
+  }
+  return st.code;
+}
+
 ligh_scheduler* ligh_scheduler_new(ligh_provider* p, int device, int max_pods, int max_adapters,
                                    int max_batch, int flush_size, int window_us, int refresh_ms,
                                    uint64_t seed, char* err, int err_cap) {
@@ -124,10 +188,11 @@ int ligh_refresh(ligh_scheduler* s, char* err, int err_cap) {
   return st.code;
 }
 
-void ligh_stats(ligh_scheduler* s, uint64_t out[7]) {
+void ligh_stats(ligh_scheduler* s, uint64_t out[9]) {
   scheduling::Stats st = s->sched->stats();
   out[0] = st.scheduled; out[1] = st.batches; out[2] = st.max_batch; out[3] = st.refreshes;
   out[4] = st.stale_retries; out[5] = st.failed_refreshes; out[6] = st.excluded_pods;
+  out[7] = st.delta_refreshes; out[8] = st.last_dirty_pods;
 }
 
 void ligh_refresh_timing(ligh_scheduler* s, double out[2]) {
@@ -170,7 +235,7 @@ int ligh_schedule_concurrent(ligh_scheduler* s, int n_threads, int per_thread,
 
 int ligh_stream_bench(ligh_scheduler* s, double rate, double seconds, int n_threads,
                       const char* const* models, const int* critical, int n_models, uint64_t seed,
-                      float* lat_us, int cap, int* n_done, int* n_errors) {
+                      float* lat_us, float* svc_us, int cap, int* n_done, int* n_errors) {
   if (!s || rate <= 0 || seconds <= 0 || n_threads < 1 || n_models < 1) return -1;
   using clock = std::chrono::steady_clock;
   std::atomic<int> slot{0}, errors{0};
@@ -200,12 +265,17 @@ int ligh_stream_bench(ligh_scheduler* s, double rate, double seconds, int n_thre
         req.Model = req.ResolvedTargetModel = models[m];
         req.Critical = critical[m] != 0;
         backend::Pod pod;
+        const auto called = clock::now();     // >= arrival: the generator itself may run late
         scheduling::Status stt = s->sched->Schedule(req, &pod);
         const auto done = clock::now();
         if (!stt.ok() && stt.code != scheduling::ResourceExhausted) errors++;
         const int i = slot.fetch_add(1);
-        if (i < cap)
+        if (i < cap) {
+          // from the SCHEDULED arrival (no coordinated omission: a late generator counts against us)
           lat_us[i] = (float)(std::chrono::duration<double, std::micro>(done - arrival).count());
+          // from the moment Schedule was actually called (the scheduler's own share)
+          if (svc_us) svc_us[i] = (float)(std::chrono::duration<double, std::micro>(done - called).count());
+        }
       }
     });
   }

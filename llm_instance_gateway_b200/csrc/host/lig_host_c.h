@@ -33,7 +33,19 @@ void ligh_scheduler_free(ligh_scheduler*);
 int ligh_schedule(ligh_scheduler*, const char* model, const char* resolved_target_model, int critical,
                   char* name, int name_cap, char* addr, int addr_cap, char* err, int err_cap);
 int ligh_refresh(ligh_scheduler*, char* err, int err_cap);
-void ligh_stats(ligh_scheduler*, uint64_t out[7]); /* scheduled, batches, max_batch, refreshes, stale_retries */
+/* several GPUs behind one scheduler (lig_group_*) */
+ligh_scheduler* ligh_scheduler_new_devices(ligh_provider*, const int* devices, int n_devices, int max_pods,
+                                           int max_adapters, int max_batch, int flush_size, int window_us,
+                                           int refresh_ms, uint64_t seed, char* err, int err_cap);
+/* a fake ModelDataStore (backend/fake.go) and the resolve + Schedule call of HandleRequestBody */
+typedef struct ligh_datastore ligh_datastore;
+ligh_datastore* ligh_datastore_new(void);
+void ligh_datastore_free(ligh_datastore*);
+int ligh_datastore_set_model(ligh_datastore*, const char* model_name, int critical, int n_targets,
+                             const char* const* target_names, const int32_t* weights);
+int ligh_schedule_model(ligh_scheduler*, ligh_datastore*, const char* model, char* resolved, int resolved_cap,
+                        char* name, int name_cap, char* addr, int addr_cap, char* err, int err_cap);
+void ligh_stats(ligh_scheduler*, uint64_t out[9]); /* scheduled, batches, max_batch, refreshes, stale_retries */
 void ligh_refresh_timing(ligh_scheduler*, double out[2]); /* last Refresh: host pack us, lig_upload_snapshot us */
 
 /* n_threads caller threads each issue `per_thread` blocking Schedule calls (model i of the
@@ -48,7 +60,7 @@ int ligh_schedule_concurrent(ligh_scheduler*, int n_threads, int per_thread,
  * lat_us[0..*n_done) (capacity cap).  Returns 0. */
 int ligh_stream_bench(ligh_scheduler*, double rate, double seconds, int n_threads,
                       const char* const* resolved_models, const int* critical, int n_models,
-                      uint64_t seed, float* lat_us, int cap, int* n_done, int* n_errors);
+                      uint64_t seed, float* lat_us, float* svc_us, int cap, int* n_done, int* n_errors);
 
 #ifdef __cplusplus
 }

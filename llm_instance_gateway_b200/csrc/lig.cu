@@ -83,6 +83,7 @@ struct Slot {
   ClassEntry* d_cls = nullptr;
   uint16_t* d_lists = nullptr;
   unsigned char* d_ctab = nullptr;  // compact tables (CompactHeader blob): entries + packed lists
+  uint32_t* d_counters = nullptr;   // pool cursor + finished-CTA counter of the build kernel
   uint32_t ctab_pool_capacity = 0;  // list entries the compact pool can hold
   CompactHeader* h_hdr = nullptr;   // pinned copy of the blob's header, valid once `ready` completed
   unsigned char* h_blob = nullptr;  // pinned staging for host uploads
@@ -123,6 +124,11 @@ struct lig_ctx {
   std::mutex bounce_mu;
   std::atomic<uint64_t> launches{0};
   void* comm = nullptr;                      // ncclComm_t, owned by lig_multi.cpp
+
+  // ---- snapshot deltas (lig_update_snapshot): pinned + device staging of one delta ----
+  unsigned char* h_delta = nullptr;
+  unsigned char* d_delta = nullptr;
+  size_t delta_capacity = 0;
 
   // ---- load feedback (lig_schedule_batch_feedback_device): a private, mutable snapshot copy ----
   std::mutex fb_mu;
@@ -260,18 +266,16 @@ int launch_class_build(lig_ctx* c, Slot& s, cudaStream_t stream) {
   if (grid > c->sm_count) grid = c->sm_count;
   if (grid < 1) grid = 1;
   const int stride = s.P > 0 ? s.P : 1;
+  CUDA_TRY(cudaMemsetAsync(s.d_counters, 0, 2 * sizeof(uint32_t), stream));
+  const CompactOut co{s.d_ctab, s.d_counters, s.ctab_pool_capacity};
   if (staged) {
-    lig_class_build_kernel<true><<<grid, kBuildThreads, smem, stream>>>(v, thr_of(c), s.d_cls, s.d_lists, stride);
+    lig_class_build_kernel<true><<<grid, kBuildThreads, smem, stream>>>(v, thr_of(c), s.d_cls, s.d_lists, stride, co);
   } else {
-    lig_class_build_kernel<false><<<grid, kBuildThreads, smem, stream>>>(v, thr_of(c), s.d_cls, s.d_lists, stride);
+    lig_class_build_kernel<false><<<grid, kBuildThreads, smem, stream>>>(v, thr_of(c), s.d_cls, s.d_lists, stride, co);
   }
   CUDA_TRY(cudaGetLastError());
   c->launches++;
-  // pack entries + lists into the compact blob and bring its header back for the launch decision
-  lig_class_compact_kernel<<<1, kCompactThreads, 0, stream>>>(s.d_cls, s.d_lists, n_classes, stride, s.d_ctab,
-                                                              s.ctab_pool_capacity);
-  CUDA_TRY(cudaGetLastError());
-  c->launches++;
+  // bring the compact blob's header back for the launch decision (tables_fit_smem)
   CUDA_TRY(cudaMemcpyAsync(s.h_hdr, s.d_ctab, sizeof(CompactHeader), cudaMemcpyDeviceToHost, stream));
   return 0;
 }
@@ -764,6 +768,7 @@ static int alloc_slot(lig_ctx* c, Slot& s) {
     CUDA_TRY(cudaMalloc(&s.d_ctab, sizeof(CompactHeader) + n_classes * sizeof(ClassEntry) + cap * sizeof(uint16_t) + 16));
     CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&s.h_hdr), sizeof(CompactHeader), cudaHostAllocDefault));
     memset(s.h_hdr, 0, sizeof(CompactHeader));
+    CUDA_TRY(cudaMalloc(&s.d_counters, 2 * sizeof(uint32_t)));
   }
   CUDA_TRY(cudaHostAlloc(&s.h_blob, l.total, cudaHostAllocDefault));
   CUDA_TRY(cudaEventCreateWithFlags(&s.ready, cudaEventDisableTiming));
@@ -777,6 +782,7 @@ static void free_slot(Slot& s) {
   cudaFree(s.d_cls);
   cudaFree(s.d_lists);
   cudaFree(s.d_ctab);
+  cudaFree(s.d_counters);
   cudaFree(s.d_mtab);
   if (s.h_mtab) cudaFreeHost(s.h_mtab);
   if (s.models_ready) cudaEventDestroy(s.models_ready);
@@ -943,6 +949,8 @@ void lig_destroy(lig_ctx* c) {
   cudaDeviceSynchronize();
   if (c->comm && ligi::g_comm_destructor) ligi::g_comm_destructor(c->comm);
   for (auto& s : c->slot) free_slot(s);
+  if (c->h_delta) cudaFreeHost(c->h_delta);
+  cudaFree(c->d_delta);
   if (c->fb_scratch.d_blob) free_slot(c->fb_scratch);
   cudaFree(c->d_fb_hist);
   if (c->fb_free) cudaEventDestroy(c->fb_free);
@@ -1014,6 +1022,89 @@ int lig_upload_snapshot(lig_ctx* c, uint64_t epoch, int P, int A, const double* 
     ligi::abort_write(c, &w);
     return rc;
   }
+  return ligi::finish_write(c, &w, true);
+}
+
+int lig_update_snapshot(lig_ctx* c, uint64_t new_epoch, uint64_t base_epoch, int n_dirty,
+                        const int32_t* pod_idx, const double* kv, const int32_t* q, const uint16_t* na,
+                        const uint16_t* ma, const int32_t* a_off, const int32_t* a_ids) {
+  if (!c || n_dirty < 0 || (n_dirty > 0 && (!pod_idx || !kv || !q || !na || !ma || !a_off)))
+    return fail(LIG_ERR_INVALID, "lig_update_snapshot: bad argument");
+  if (new_epoch == base_epoch) return fail(LIG_ERR_INVALID, "lig_update_snapshot: new_epoch == base_epoch");
+  const int n_ids = n_dirty ? a_off[n_dirty] : 0;
+  if (n_ids < 0 || (n_ids > 0 && !a_ids)) return fail(LIG_ERR_INVALID, "lig_update_snapshot: bad adapter arrays");
+  int P = 0, A = 0;
+  {
+    std::lock_guard<std::mutex> lk(c->mu);
+    Slot* b = nullptr;
+    if (int rc = resolve_slot(c, base_epoch, &b)) return rc;
+    P = b->P;
+    A = b->A;
+    // the slot the new epoch will overwrite must not be the base
+    if (&victim_slot(c, new_epoch) == b)
+      return fail(LIG_ERR_INVALID, "base epoch %llu is the slot epoch %llu would overwrite: use lig_upload_snapshot",
+                  (unsigned long long)base_epoch, (unsigned long long)new_epoch);
+  }
+  for (int i = 0; i < n_dirty; ++i)
+    if (pod_idx[i] < 0 || pod_idx[i] >= P) return fail(LIG_ERR_INVALID, "dirty pod index %d outside [0, %d)", pod_idx[i], P);
+  ligi::SnapshotWrite w;
+  if (int rc = ligi::begin_write(c, new_epoch, P, A, nullptr, true, &w)) return rc;
+  // from here on failures must release the writer lock
+  auto bail = [&](int rc) { ligi::abort_write(c, &w); return rc; };
+  // layout of the staged delta: pod_idx | q | a_off | a_ids | kv | n_active | max_active
+  const size_t o_idx = 0, o_q = o_idx + (size_t)n_dirty * 4, o_off = o_q + (size_t)n_dirty * 4,
+               o_ids = o_off + ((size_t)n_dirty + 1) * 4, o_kv = (o_ids + (size_t)n_ids * 4 + 7) & ~(size_t)7,
+               o_na = o_kv + (size_t)n_dirty * 8, o_ma = o_na + (size_t)n_dirty * 2,
+               total = (o_ma + (size_t)n_dirty * 2 + 15) & ~(size_t)15;
+  if (total > c->delta_capacity) {
+    if (c->stream_open) return bail(fail(LIG_ERR_INVALID, "cannot grow the delta staging while a doorbell stream is open"));
+    if (cudaStreamSynchronize(w.stream) != cudaSuccess) return bail(fail(LIG_ERR_CUDA, "stream synchronise failed"));
+    if (c->h_delta) cudaFreeHost(c->h_delta);
+    cudaFree(c->d_delta);
+    c->h_delta = nullptr;
+    c->d_delta = nullptr;
+    c->delta_capacity = 0;
+    const size_t cap = total * 2 + 4096;
+    if (cudaHostAlloc(reinterpret_cast<void**>(&c->h_delta), cap, cudaHostAllocDefault) != cudaSuccess ||
+        cudaMalloc(reinterpret_cast<void**>(&c->d_delta), cap) != cudaSuccess)
+      return bail(fail(LIG_ERR_CUDA, "delta staging allocation failed"));
+    c->delta_capacity = cap;
+  }
+  Slot* base = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (int rc = resolve_slot(c, base_epoch, &base)) return bail(rc);
+    if (base == static_cast<Slot*>(w.slot)) return bail(fail(LIG_ERR_INVALID, "base epoch was evicted meanwhile"));
+    if (cudaStreamWaitEvent(w.stream, base->ready, 0) != cudaSuccess) return bail(fail(LIG_ERR_CUDA, "cudaStreamWaitEvent failed"));
+    if (cudaMemcpyAsync(w.d_blob, base->d_blob, w.bytes, cudaMemcpyDeviceToDevice, w.stream) != cudaSuccess)
+      return bail(fail(LIG_ERR_CUDA, "base snapshot copy failed"));
+    if (int rc = note_reader(*base, w.stream)) return bail(rc);     // a later overwrite of the base waits for this copy
+  }
+  if (n_dirty > 0) {
+    unsigned char* h = c->h_delta;     // the previous delta upload synchronised before returning
+    memcpy(h + o_idx, pod_idx, (size_t)n_dirty * 4);
+    memcpy(h + o_q, q, (size_t)n_dirty * 4);
+    memcpy(h + o_off, a_off, ((size_t)n_dirty + 1) * 4);
+    if (n_ids) memcpy(h + o_ids, a_ids, (size_t)n_ids * 4);
+    memcpy(h + o_kv, kv, (size_t)n_dirty * 8);
+    memcpy(h + o_na, na, (size_t)n_dirty * 2);
+    memcpy(h + o_ma, ma, (size_t)n_dirty * 2);
+    if (cudaMemcpyAsync(c->d_delta, h, total, cudaMemcpyHostToDevice, w.stream) != cudaSuccess)
+      return bail(fail(LIG_ERR_CUDA, "delta H2D copy failed"));
+    const unsigned char* dd = c->d_delta;
+    DeltaView dv{reinterpret_cast<const int*>(dd + o_idx), reinterpret_cast<const double*>(dd + o_kv),
+                 reinterpret_cast<const int*>(dd + o_q), reinterpret_cast<const uint16_t*>(dd + o_na),
+                 reinterpret_cast<const uint16_t*>(dd + o_ma), reinterpret_cast<const int*>(dd + o_off),
+                 reinterpret_cast<const int*>(dd + o_ids), n_dirty};
+    const Layout l = layout_for(P, A);
+    lig_apply_delta_kernel<<<(n_dirty * 32 + 255) / 256, 256, 0, w.stream>>>(
+        dv, reinterpret_cast<double*>(w.d_blob + l.kv), reinterpret_cast<int*>(w.d_blob + l.q),
+        reinterpret_cast<uint16_t*>(w.d_blob + l.na), reinterpret_cast<uint16_t*>(w.d_blob + l.ma),
+        reinterpret_cast<uint32_t*>(w.d_blob + l.bitmap), P, A, words_for(P));
+    if (cudaGetLastError() != cudaSuccess) return bail(fail(LIG_ERR_CUDA, "delta kernel launch failed"));
+    c->launches++;
+  }
+  if (int rc = ligi::enqueue_build(c, &w)) return bail(rc);
   return ligi::finish_write(c, &w, true);
 }
 

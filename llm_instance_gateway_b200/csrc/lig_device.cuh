@@ -645,10 +645,35 @@ __device__ __forceinline__ ClassEntry make_entry(uint32_t n, uint32_t status, ui
   return e;
 }
 
+// ---- compact tables -----------------------------------------------------------------------------
+// The survivor lists are tiny in practice (a handful of pods per class after the least-KV stage).
+// Besides the strided rows (one row of P entries per class: every warp works alone, and
+// lig_read_class can address a class directly) the build packs them behind a copy of the class
+// entries into ONE contiguous blob that the persistent pick kernels pull into shared memory with a
+// single TMA bulk copy:
+//
+//   [ header 16 B ][ entries: n_classes x 16 B, list_off relative to the pool ][ pool: u16[] ]
+//
+// pool[0] is the 0xffff sentinel (pod_idx -1) every class without survivors points at, then the
+// two default lists (stored once), then the own lists in the order their warps finished (pool
+// space is handed out by an atomic cursor).  If the pool does not fit `pool_capacity` entries the
+// header says so (bytes = 0) and the pick kernels keep to the strided tables in global memory.
+struct CompactHeader {
+  uint32_t bytes;         // header + entries + pool, rounded up to 16; 0 = not available
+  uint32_t n_classes;
+  uint32_t pool_entries;
+  uint32_t reserved;
+};
+struct CompactOut {       // where the build writes the blob; counters[0] = pool cursor of the own
+  unsigned char* blob;    // lists, counters[1] = finished CTAs (both zeroed before the launch)
+  uint32_t* counters;
+  uint32_t pool_capacity;
+};
+
 template <bool kStaged>
 __global__ void __launch_bounds__(kBuildThreads)
 lig_class_build_kernel(SnapView s, Thr thr, ClassEntry* __restrict__ cls,
-                       uint16_t* __restrict__ lists, int list_stride) {
+                       uint16_t* __restrict__ lists, int list_stride, CompactOut co) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int P = s.P, W = s.W, A = s.A;
@@ -672,10 +697,35 @@ lig_class_build_kernel(SnapView s, Thr thr, ClassEntry* __restrict__ cls,
   const uint32_t rs_row = rc_row + (uint32_t)list_stride;
   const uint32_t none = rs_row + (uint32_t)list_stride;                       // sentinel entry
   if (blockIdx.x == 0 && threadIdx.x == 0) lists[none] = 0xffffu;             // reads back as pod_idx -1
+  CompactHeader* chdr = reinterpret_cast<CompactHeader*>(co.blob);
+  uint4* centries = reinterpret_cast<uint4*>(co.blob + sizeof(CompactHeader));
+  uint16_t* cpool = reinterpret_cast<uint16_t*>(co.blob + sizeof(CompactHeader) + (size_t)n_classes * sizeof(ClassEntry));
+  // the last CTA to finish seals the blob: total size, or 0 when the pool overflowed
+  auto seal = [&](uint32_t fixed_entries) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      if (atomicAdd(co.counters + 1, 1u) == gridDim.x - 1) {
+        __threadfence();
+        const uint32_t total = fixed_entries + *reinterpret_cast<volatile uint32_t*>(co.counters);
+        chdr->n_classes = (uint32_t)n_classes;
+        chdr->pool_entries = total;
+        chdr->reserved = 0;
+        chdr->bytes = total <= co.pool_capacity
+                          ? (uint32_t)((sizeof(CompactHeader) + (size_t)n_classes * sizeof(ClassEntry) +
+                                        (size_t)total * sizeof(uint16_t) + 15) & ~(size_t)15) : 0u;
+      }
+    }
+  };
 
   if (P == 0) {   // critical: predicate node errs on an empty pool -> sheddable branch -> drop
-    for (int c = blockIdx.x * kBuildThreads + threadIdx.x; c < n_classes; c += gridDim.x * kBuildThreads)
-      cls[c] = make_entry(0u, (uint32_t)LIG_DROP, none);
+    for (int c = blockIdx.x * kBuildThreads + threadIdx.x; c < n_classes; c += gridDim.x * kBuildThreads) {
+      const ClassEntry e = make_entry(0u, (uint32_t)LIG_DROP, none);
+      cls[c] = e;
+      centries[c] = make_uint4(e.info, e.magic, e.q_limit, 0u);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) cpool[0] = 0xffffu;
+    seal(1u);
     return;
   }
 
@@ -719,7 +769,10 @@ lig_class_build_kernel(SnapView s, Thr thr, ClassEntry* __restrict__ cls,
     nc = blk_least_queuing<kStaged>(f, TMP, W, nc, sh, warp, lane);
     rc_n = blk_least_kv<kStaged>(f, TMP, W, nc, sh, warp, lane);
     rc_status = rc_n ? LIG_OK : LIG_EMPTY;
-    if (blockIdx.x == 0 && warp == 0 && rc_n) compact_mask_to_list(TMP, W, lane, lists + rc_row);
+    if (blockIdx.x == 0 && warp == 0 && rc_n) {
+      compact_mask_to_list(TMP, W, lane, lists + rc_row);
+      compact_mask_to_list(TMP, W, lane, cpool + 1);
+    }
     __syncthreads();
   } else {
     // low-queue filter failed: all pods -> least queuing -> low cost LoRA -> least KV  scheduler.go:71,35-46
@@ -739,7 +792,10 @@ lig_class_build_kernel(SnapView s, Thr thr, ClassEntry* __restrict__ cls,
     __syncthreads();
     rc_n = blk_least_kv<kStaged>(f, TMP, W, ny, sh, warp, lane);
     rc_status = rc_n ? LIG_OK : LIG_EMPTY;
-    if (blockIdx.x == 0 && warp == 0 && rc_n) compact_mask_to_list(TMP, W, lane, lists + rc_row);
+    if (blockIdx.x == 0 && warp == 0 && rc_n) {
+      compact_mask_to_list(TMP, W, lane, lists + rc_row);
+      compact_mask_to_list(TMP, W, lane, cpool + 1);
+    }
     __syncthreads();
   }
   // sheddable side: "has capacity for sheddable requests"                 scheduler.go:74-79
@@ -762,9 +818,14 @@ lig_class_build_kernel(SnapView s, Thr thr, ClassEntry* __restrict__ cls,
     __syncthreads();
     rs_n = blk_least_kv<kStaged>(f, TMP, W, ny, sh, warp, lane);
     rs_status = rs_n ? LIG_OK : LIG_EMPTY;
-    if (blockIdx.x == 0 && warp == 0 && rs_n) compact_mask_to_list(TMP, W, lane, lists + rs_row);
+    if (blockIdx.x == 0 && warp == 0 && rs_n) {
+      compact_mask_to_list(TMP, W, lane, lists + rs_row);
+      compact_mask_to_list(TMP, W, lane, cpool + 1 + rc_n);
+    }
   }
   __syncthreads();
+  if (blockIdx.x == 0 && threadIdx.x == 0) cpool[0] = 0xffffu;
+  const uint32_t fixed_entries = 1u + rc_n + rs_n;   // sentinel + the two default lists
 
   // ---- per class (one warp each): AND the adapter row with the shared mask --------------------
   for (int c = blockIdx.x * kBuildWarps + warp; c < n_classes; c += gridDim.x * kBuildWarps) {
@@ -772,6 +833,7 @@ lig_class_build_kernel(SnapView s, Thr thr, ClassEntry* __restrict__ cls,
     const int a = critical ? c - (A + 1) : c;
     const uint32_t* row = a < A ? s.bitmap + (size_t)a * W : nullptr;
     ClassEntry e;
+    uint32_t coff = 0;                   // the class's list in the compact pool (0 = the sentinel)
     if (!critical && n_shed == 0) {
       e = make_entry(0u, (uint32_t)LIG_DROP, none);                        // scheduler.go:83-89
     } else {
@@ -789,6 +851,7 @@ lig_class_build_kernel(SnapView s, Thr thr, ClassEntry* __restrict__ cls,
       if (hit == 0) {
         e = critical ? make_entry(rc_n, rc_status, rc_n ? rc_row : none)
                      : make_entry(rs_n, rs_status, rs_n ? rs_row : none);
+        coff = critical ? (rc_n ? 1u : 0u) : (rs_n ? 1u + rc_n : 0u);
       } else {
         uint32_t n = hit;
         if (Zm) {   // low cost LoRA: (affinity | room) on the least-queuing set     filter.go:163-166
@@ -805,110 +868,63 @@ lig_class_build_kernel(SnapView s, Thr thr, ClassEntry* __restrict__ cls,
           n = sparse_least_queuing<kStaged>(f, X, W, lane, n);
         n = sparse_least_kv<kStaged>(f, X, W, lane, n);
         const uint32_t off = (uint32_t)c * (uint32_t)list_stride;
-        if (n) compact_mask_to_list(X, W, lane, lists + off);
+        if (n) {
+          compact_mask_to_list(X, W, lane, lists + off);
+          uint32_t at = 0;
+          if (lane == 0) at = atomicAdd(co.counters, n);           // pool space for this list
+          at = __shfl_sync(kFull, at, 0) + fixed_entries;
+          if (at + n <= co.pool_capacity) compact_mask_to_list(X, W, lane, cpool + at);
+          coff = at;
+        }
         e = make_entry(n, n ? (uint32_t)LIG_OK : (uint32_t)LIG_EMPTY, n ? off : none);
       }
     }
-    if (lane == 0) *reinterpret_cast<uint4*>(cls + c) = make_uint4(e.info, e.magic, e.q_limit, e.list_off);
+    if (lane == 0) {
+      *reinterpret_cast<uint4*>(cls + c) = make_uint4(e.info, e.magic, e.q_limit, e.list_off);
+      centries[c] = make_uint4(e.info, e.magic, e.q_limit, coff);
+    }
     __syncwarp();
   }
+  seal(fixed_entries);
 }
 
-// ---- K2a': compact tables ---------------------------------------------------------------------------
-// The survivor lists are tiny in practice (a handful of pods per class after the least-KV stage),
-// but the build above writes them at a stride of P entries so that every warp can work alone.
-// This pass (one CTA, once per snapshot) packs them behind the class entries into ONE contiguous
-// blob that the persistent pick kernels pull into shared memory with a single TMA bulk copy:
-//
-//   [ header 16 B ][ entries: n_classes x 16 B, list_off relative to the pool ][ pool: u16[] ]
-//
-// pool[0] is the 0xffff sentinel (pod_idx -1) every class without survivors points at.  The two
-// default lists are stored once.  If the pool does not fit `pool_capacity` entries the header says
-// so and the pick kernels fall back to the strided tables in global memory.
-struct CompactHeader {
-  uint32_t bytes;         // header + entries + pool, rounded up to 16; 0 = not available
-  uint32_t n_classes;
-  uint32_t pool_entries;
-  uint32_t reserved;
+// ---- snapshot delta ---------------------------------------------------------------------------------
+// One warp per dirty pod: overwrite its four column values, clear its bit in every adapter row,
+// set it again in the rows of its new ActiveModels.  Different pods may share a bitmap word, hence
+// the atomics; a pod appears at most once in a delta.
+struct DeltaView {
+  const int* pod_idx;
+  const double* kv;
+  const int* q;
+  const uint16_t* n_active;
+  const uint16_t* max_active;
+  const int* adapter_offsets;   // n_dirty + 1
+  const int* adapter_ids;
+  int n_dirty;
 };
-constexpr int kCompactThreads = 1024;
 
-__global__ void __launch_bounds__(kCompactThreads)
-lig_class_compact_kernel(const ClassEntry* __restrict__ cls, const uint16_t* __restrict__ lists,
-                         int n_classes, int list_stride, unsigned char* __restrict__ blob,
-                         uint32_t pool_capacity) {
-  __shared__ uint32_t warp_sums[kCompactThreads / 32];
-  __shared__ uint32_t carry;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  CompactHeader* hdr = reinterpret_cast<CompactHeader*>(blob);
-  uint4* out = reinterpret_cast<uint4*>(blob + sizeof(CompactHeader));
-  uint16_t* pool = reinterpret_cast<uint16_t*>(blob + sizeof(CompactHeader) + (size_t)n_classes * sizeof(ClassEntry));
-  const uint32_t rc_row = (uint32_t)n_classes * (uint32_t)list_stride;
-  const uint32_t rs_row = rc_row + (uint32_t)list_stride;
-  // the default lists first: their lengths are the n of any class that points at them
-  // (items -2 and -1 of the scan), found by a block-wide search
-  __shared__ uint32_t def_n[2];
-  if (threadIdx.x < 2) def_n[threadIdx.x] = 0;
-  if (threadIdx.x == 0) carry = 1;                       // pool[0] = sentinel
-  __syncthreads();
-  for (int c = threadIdx.x; c < n_classes; c += kCompactThreads) {
-    const ClassEntry e = cls[c];
-    const uint32_t n = entry_n(e.info);
-    if (n && e.list_off == rc_row) def_n[0] = n;         // same value from every writer
-    if (n && e.list_off == rs_row) def_n[1] = n;
+__global__ void lig_apply_delta_kernel(DeltaView d, double* __restrict__ kv, int* __restrict__ q,
+                                       uint16_t* __restrict__ n_active, uint16_t* __restrict__ max_active,
+                                       uint32_t* __restrict__ bitmap, int P, int A, int W) {
+  const int lane = threadIdx.x & 31;
+  const int i = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (i >= d.n_dirty) return;
+  const int p = d.pod_idx[i];
+  if (p < 0 || p >= P) return;
+  if (lane == 0) {
+    kv[p] = d.kv[i];
+    q[p] = d.q[i];
+    n_active[p] = d.n_active[i];
+    max_active[p] = d.max_active[i];
   }
-  __syncthreads();
-  const uint32_t off_rc = 1, off_rs = 1 + def_n[0];
-  if (threadIdx.x == 0) carry = 1 + def_n[0] + def_n[1];
-  __syncthreads();
-  // exclusive scan of the own-row list lengths, kCompactThreads classes per round
-  for (int base = 0; base < n_classes; base += kCompactThreads) {
-    const int c = base + threadIdx.x;
-    ClassEntry e{0, 0, 1, 0};
-    uint32_t n = 0, own = 0;
-    if (c < n_classes) {
-      e = cls[c];
-      n = entry_n(e.info);
-      own = (n && e.list_off == (uint32_t)c * (uint32_t)list_stride) ? n : 0;
-    }
-    uint32_t incl = own;
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-      const uint32_t o = __shfl_up_sync(kFull, incl, off);
-      if (lane >= off) incl += o;
-    }
-    if (lane == 31) warp_sums[warp] = incl;
-    __syncthreads();
-    uint32_t before = carry;
-    for (int w = 0; w < warp; ++w) before += warp_sums[w];
-    const uint32_t my_off = before + incl - own;
-    __syncthreads();
-    if (threadIdx.x == kCompactThreads - 1) carry = before + incl;
-    if (c < n_classes) {
-      uint32_t off = 0;                                   // no survivors -> the sentinel
-      if (own) {
-        off = my_off;
-        if (my_off + own <= pool_capacity)
-          for (uint32_t k = 0; k < own; ++k) pool[my_off + k] = lists[e.list_off + k];
-      } else if (n) {
-        off = e.list_off == rc_row ? off_rc : off_rs;
-      }
-      out[c] = make_uint4(e.info, e.magic, e.q_limit, off);
-    }
-    __syncthreads();
-  }
-  // the default lists and the sentinel
-  for (uint32_t k = threadIdx.x; k < def_n[0]; k += kCompactThreads) pool[off_rc + k] = lists[rc_row + k];
-  for (uint32_t k = threadIdx.x; k < def_n[1]; k += kCompactThreads) pool[off_rs + k] = lists[rs_row + k];
-  if (threadIdx.x == 0) {
-    pool[0] = 0xffffu;
-    const uint32_t total = carry;
-    const uint32_t bytes = (uint32_t)((sizeof(CompactHeader) + (size_t)n_classes * sizeof(ClassEntry) +
-                                       (size_t)total * sizeof(uint16_t) + 15) & ~(size_t)15);
-    hdr->n_classes = (uint32_t)n_classes;
-    hdr->pool_entries = total;
-    hdr->reserved = 0;
-    hdr->bytes = total <= pool_capacity ? bytes : 0u;
+  const uint32_t bit = 1u << (p & 31);
+  uint32_t* col = bitmap + (p >> 5);
+  for (int a = lane; a < A; a += 32)
+    if (col[(size_t)a * W] & bit) atomicAnd(col + (size_t)a * W, ~bit);
+  __syncwarp();
+  for (int k = d.adapter_offsets[i] + lane; k < d.adapter_offsets[i + 1]; k += 32) {
+    const int a = d.adapter_ids[k];
+    if (a >= 0 && a < A) atomicOr(col + (size_t)a * W, bit);
   }
 }
 

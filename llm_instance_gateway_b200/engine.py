@@ -53,6 +53,15 @@ class Engine:
                                               _ptr(snap.q), _ptr(snap.n_active),
                                               _ptr(snap.max_active), _ptr(snap.bitmap)))
 
+    def update_snapshot(self, new_epoch: int, base_epoch: int, pod_idx, kv, q, n_active, max_active,
+                        adapter_offsets, adapter_ids) -> None:
+        """Delta upload: base_epoch with the listed pods replaced becomes new_epoch."""
+        a = [np.ascontiguousarray(pod_idx, dtype=np.int32), np.ascontiguousarray(kv, dtype=np.float64),
+             np.ascontiguousarray(q, dtype=np.int32), np.ascontiguousarray(n_active, dtype=np.uint16),
+             np.ascontiguousarray(max_active, dtype=np.uint16), np.ascontiguousarray(adapter_offsets, dtype=np.int32),
+             np.ascontiguousarray(adapter_ids, dtype=np.int32)]
+        N.check(self._lib.lig_update_snapshot(self._ctx, new_epoch, base_epoch, len(a[0]), *[_ptr(x) for x in a]))
+
     def upload_snapshot_device(self, epoch: int, P: int, A: int, d_blob: int, stream: int = 0) -> None:
         N.check(self._lib.lig_upload_snapshot_device(self._ctx, epoch, P, A, d_blob, stream or None))
 

@@ -25,6 +25,8 @@ EXPORTED_SYMBOLS = (
     "ligh_scheduler_new2",
     "ligh_scheduler_free", "ligh_schedule", "ligh_refresh", "ligh_stats",
     "ligh_schedule_concurrent", "ligh_stream_bench", "ligh_refresh_timing",
+    "ligh_scheduler_new_devices", "ligh_datastore_new", "ligh_datastore_free", "ligh_datastore_set_model",
+    "ligh_schedule_model",
 )
 
 _lib = None
@@ -47,6 +49,13 @@ def load() -> C.CDLL:
     lib.ligh_scheduler_new.restype = vp
     lib.ligh_scheduler_new2.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, u64, i32, i32, i32, C.c_char_p, i32]
     lib.ligh_scheduler_new2.restype = vp
+    lib.ligh_scheduler_new_devices.argtypes = [vp, C.POINTER(i32), i32, i32, i32, i32, i32, i32, i32, u64, C.c_char_p, i32]
+    lib.ligh_scheduler_new_devices.restype = vp
+    lib.ligh_datastore_new.restype = vp
+    lib.ligh_datastore_free.argtypes = [vp]
+    lib.ligh_datastore_free.restype = None
+    lib.ligh_datastore_set_model.argtypes = [vp, C.c_char_p, i32, i32, cpp, vp]
+    lib.ligh_schedule_model.argtypes = [vp, vp, C.c_char_p, C.c_char_p, i32, C.c_char_p, i32, C.c_char_p, i32, C.c_char_p, i32]
     lib.ligh_scheduler_free.argtypes = [vp]
     lib.ligh_scheduler_free.restype = None
     lib.ligh_schedule.argtypes = [vp, C.c_char_p, C.c_char_p, i32, C.c_char_p, i32, C.c_char_p, i32,
@@ -57,7 +66,7 @@ def load() -> C.CDLL:
     lib.ligh_refresh_timing.argtypes = [vp, vp]
     lib.ligh_refresh_timing.restype = None
     lib.ligh_schedule_concurrent.argtypes = [vp, i32, i32, cpp, vp, i32, vp, vp]
-    lib.ligh_stream_bench.argtypes = [vp, C.c_double, C.c_double, i32, cpp, vp, i32, u64, vp, i32,
+    lib.ligh_stream_bench.argtypes = [vp, C.c_double, C.c_double, i32, cpp, vp, i32, u64, vp, vp, i32,
                                       C.POINTER(i32), C.POINTER(i32)]
     for name in EXPORTED_SYMBOLS:
         getattr(lib, name)
@@ -111,13 +120,20 @@ class HostScheduler:
     def __init__(self, provider: HostProvider, device: int = 0, max_pods: int = 4096,
                  max_adapters: int = 1024, max_batch: int = 1 << 16, flush_size: int = 4096,
                  batch_window_us: int = 50, refresh_interval_ms: int = 0, seed: int = 1,
-                 busy_poll: bool = False, caller_spin_us: int = 0, use_doorbell: bool = False):
+                 busy_poll: bool = False, caller_spin_us: int = 0, use_doorbell: bool = False,
+                 devices: Optional[Sequence[int]] = None):
         self._lib = load()
         self.provider = provider
         err = C.create_string_buffer(512)
-        self._s = self._lib.ligh_scheduler_new2(provider._p, device, max_pods, max_adapters, max_batch,
-                                                flush_size, batch_window_us, refresh_interval_ms, seed,
-                                                int(busy_poll), caller_spin_us, int(use_doorbell), err, 512)
+        if devices is not None and len(devices) > 1:
+            arr = (C.c_int * len(devices))(*devices)
+            self._s = self._lib.ligh_scheduler_new_devices(provider._p, arr, len(devices), max_pods, max_adapters,
+                                                           max_batch, flush_size, batch_window_us, refresh_interval_ms,
+                                                           seed, err, 512)
+        else:
+            self._s = self._lib.ligh_scheduler_new2(provider._p, device, max_pods, max_adapters, max_batch,
+                                                    flush_size, batch_window_us, refresh_interval_ms, seed,
+                                                    int(busy_poll), caller_spin_us, int(use_doorbell), err, 512)
         if not self._s:
             raise HostSchedulerError(err.value.decode("utf-8", "replace"))
 
@@ -141,10 +157,18 @@ class HostScheduler:
             raise HostSchedulerError(err.value.decode())
 
     def stats(self) -> dict:
-        out = (C.c_uint64 * 7)()
+        out = (C.c_uint64 * 9)()
         self._lib.ligh_stats(self._s, out)
         return dict(zip(("scheduled", "batches", "max_batch", "refreshes", "stale_retries", "failed_refreshes",
-                         "excluded_pods"), map(int, out)))
+                         "excluded_pods", "delta_refreshes", "last_dirty_pods"), map(int, out)))
+
+    def ScheduleModel(self, datastore: "HostDataStore", model: str):  # noqa: N802
+        """resolve (FetchModelData + RandomWeightedDraw + IsCritical) + Schedule: (code, resolved, pod, err)."""
+        resolved, name, addr = C.create_string_buffer(256), C.create_string_buffer(256), C.create_string_buffer(256)
+        err = C.create_string_buffer(512)
+        code = self._lib.ligh_schedule_model(self._s, datastore._d, model.encode(), resolved, 256, name, 256, addr, 256, err, 512)
+        pod = Pod(name.value.decode(), addr.value.decode()) if code == GRPC_OK else None
+        return code, resolved.value.decode(), pod, err.value.decode("utf-8", "replace")
 
     def refresh_timing(self) -> dict:
         out = (C.c_double * 2)()
@@ -167,10 +191,34 @@ class HostScheduler:
                      critical: Sequence[bool], seed: int = 1):
         cap = int(rate * seconds * 1.2) + 1024
         lat = np.zeros(cap, dtype=np.float32)
+        svc = np.zeros(cap, dtype=np.float32)
         crit = np.array([int(c) for c in critical], dtype=np.int32)
         n_done, n_err = C.c_int(), C.c_int()
         rc = self._lib.ligh_stream_bench(self._s, rate, seconds, n_threads, _strs(models),
-                                         crit.ctypes.data, len(models), seed, lat.ctypes.data, cap,
+                                         crit.ctypes.data, len(models), seed, lat.ctypes.data, svc.ctypes.data, cap,
                                          C.byref(n_done), C.byref(n_err))
         assert rc == 0
+        self.last_service_latency_us = svc[: n_done.value].copy()
         return lat[: n_done.value].copy(), n_err.value
+
+
+class HostDataStore:
+    """backend.FakeDataStore on the C++ side: model name -> InferenceModel."""
+
+    def __init__(self, models=()):
+        self._lib = load()
+        self._d = self._lib.ligh_datastore_new()
+        for m in models:
+            self.set_model(m)
+
+    def set_model(self, m) -> None:
+        tms = m.Spec.TargetModels
+        w = np.array([t.Weight for t in tms], dtype=np.int32)
+        rc = self._lib.ligh_datastore_set_model(self._d, m.Spec.ModelName.encode(), int(m.Spec.Criticality == "Critical"),
+                                                len(tms), _strs([t.Name for t in tms]), w.ctypes.data if len(tms) else None)
+        assert rc == 0
+
+    def close(self):
+        if self._d:
+            self._lib.ligh_datastore_free(self._d)
+            self._d = None
