@@ -107,6 +107,14 @@ def make_requests(R: int, A: int, seed: int = REQUEST_SEED, out: np.ndarray = No
     return reqs
 
 
+def shard_bounds(total: int, rank: int, world: int):
+    """Contiguous request shard [lo, hi) of rank `rank` (what lig_group_schedule_batch and bench.py
+    use): result order == request order, sizes differ by at most one."""
+    if world < 1 or not (0 <= rank < world) or total < 0:
+        raise ValueError("bad shard arguments")
+    return total * rank // world, total * (rank + 1) // world
+
+
 def algorithmic_bytes(R: int, P: int, A: int) -> int:
     """24 R + 16 P + 4 A ceil(P/32)  (SURVEY.md section 8d)."""
     return 24 * R + 16 * P + 4 * A * ((P + 31) // 32)

@@ -59,8 +59,12 @@ def test_gpu_arm_contract():
     e = d["e2e"]
     assert e["value"] > 0 and e["h2d_bytes_per_step"] >= 4 * 65536 and e["d2h_bytes_per_step"] == 4 * 65536
     assert e["value"] < d["value"] and e["descriptor_call"]["d2h_bytes_per_step"] == 8 * 65536
-    assert set(d["k_sweep"]) == {"1", "20", "200"} and d["strong"]["requests_per_gpu"] == 65536
+    assert {"1", "20", "200"} <= set(d["k_sweep"]) and d["strong"]["requests_per_gpu"] == 65536
     assert d["snapshot_tick"]["us"] > 0 and d["adapter_dist_uniform"]["value"] > 0 and d["model_requests"]["value"] > 0
+    assert d["k_sweep"]["launch_floor_us"] > 0 and d["strong"]["k200"]["value"] > 0
+    fb = d["load_feedback"]
+    assert fb["max_picks_per_pod"]["with_feedback"] <= fb["max_picks_per_pod"]["default"]
+    assert fb["pods_used"]["with_feedback"] >= fb["pods_used"]["default"]
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] > 0
     assert cb["class_table_cpu"]["value"] > cb["optimised_cpu"]["value"] > cb["single_thread"]["value"]
