@@ -85,7 +85,8 @@ struct Slot {
   unsigned char* d_ctab = nullptr;  // compact tables (CompactHeader blob): entries + packed lists
   uint32_t* d_counters = nullptr;   // pool cursor + finished-CTA counter of the build kernel
   uint32_t ctab_pool_capacity = 0;  // list entries the compact pool can hold
-  CompactHeader* h_hdr = nullptr;   // pinned copy of the blob's header, valid once `ready` completed
+  CompactHeader* h_hdr = nullptr;   // pinned, device-mapped copy of the blob's header, valid once `ready` completed
+  CompactHeader* d_hdr_alias = nullptr;   // its device-visible address
   unsigned char* h_blob = nullptr;  // pinned staging for host uploads
   // model table of this epoch (lig_upload_models), grown on demand
   unsigned char* d_mtab = nullptr;
@@ -178,6 +179,7 @@ struct lig_ctx {
   int tma_groups = 2;               // LIG_TMA_GROUPS = 1|2|3 consumer groups of 8 warps per CTA
   int tma_stages = 2;               // LIG_TMA_STAGES = 2|3|4|6 ring stages of 16 KB per CTA (a multiple of the groups)
   bool tma_bulk_store = false;      // LIG_TMA_BULK_STORE=1: picks leave through TMA bulk stores
+  bool fast_build = true;           // LIG_FAST_BUILD=0: always the general class-build kernel
   bool tab_smem = true;             // LIG_TAB_SMEM=0: never pull the compact tables into shared memory
   int models_groups = 2;            // LIG_MODELS_GROUPS = 1|2, LIG_MODELS_STAGES = 2|4|8 (4 KB stages)
   int models_stages = 4;
@@ -266,17 +268,36 @@ int launch_class_build(lig_ctx* c, Slot& s, cudaStream_t stream) {
   if (grid > c->sm_count) grid = c->sm_count;
   if (grid < 1) grid = 1;
   const int stride = s.P > 0 ? s.P : 1;
-  CUDA_TRY(cudaMemsetAsync(s.d_counters, 0, 2 * sizeof(uint32_t), stream));
-  const CompactOut co{s.d_ctab, s.d_counters, s.ctab_pool_capacity};
-  if (staged) {
+  // the pool cursor / finished-CTA counters are zero at allocation and reset by the sealing CTA
+  static unsigned long long* dbg = nullptr;   // LIG_BUILD_DEBUG=1: phase stamps of the fast build
+  static bool dbg_on = getenv("LIG_BUILD_DEBUG") != nullptr;
+  if (dbg_on && !dbg) {
+    cudaHostAlloc(reinterpret_cast<void**>(&dbg), 16 * sizeof(unsigned long long), cudaHostAllocMapped);
+    memset(dbg, 0, 16 * sizeof(unsigned long long));
+  }
+  if (dbg_on && dbg[7]) {
+    fprintf(stderr, "lig build stamps (cycles): stage %llu | own pods %llu | counts %llu | crit stages %llu | masks+shed %llu | classes %llu | seal %llu | total %llu\n",
+            dbg[1] - dbg[0], dbg[2] - dbg[1], dbg[3] - dbg[2], dbg[4] - dbg[3], dbg[5] - dbg[4], dbg[6] - dbg[5], dbg[7] - dbg[6], dbg[7] - dbg[0]);
+    dbg[7] = 0;
+  }
+  const CompactOut co{s.d_ctab, s.d_counters, s.ctab_pool_capacity, s.d_hdr_alias, dbg};
+  const bool fast = c->fast_build && s.P > 0 && W <= kFastMaxWords &&
+                    fast_fixed_bytes(W) + staged_bytes(W) <= c->smem_optin;
+  if (fast) {
+    // pools of up to 4096 pods: register-resident shared stages, one class per warp
+    int fgrid = (n_classes + kBuildWarps - 1) / kBuildWarps;
+    if (fgrid > c->sm_count) fgrid = c->sm_count;
+    lig_class_build_fast_kernel<<<fgrid, kBuildThreads, fast_fixed_bytes(W) + staged_bytes(W), stream>>>(
+        v, thr_of(c), s.d_cls, s.d_lists, stride, co);
+  } else if (staged) {
     lig_class_build_kernel<true><<<grid, kBuildThreads, smem, stream>>>(v, thr_of(c), s.d_cls, s.d_lists, stride, co);
   } else {
     lig_class_build_kernel<false><<<grid, kBuildThreads, smem, stream>>>(v, thr_of(c), s.d_cls, s.d_lists, stride, co);
   }
   CUDA_TRY(cudaGetLastError());
   c->launches++;
-  // bring the compact blob's header back for the launch decision (tables_fit_smem)
-  CUDA_TRY(cudaMemcpyAsync(s.h_hdr, s.d_ctab, sizeof(CompactHeader), cudaMemcpyDeviceToHost, stream));
+  // the sealing CTA also writes the compact blob's header to s.h_hdr (mapped host memory): the
+  // host reads it once `ready` has completed to decide whether the tables go to shared memory
   return 0;
 }
 
@@ -766,9 +787,11 @@ static int alloc_slot(lig_ctx* c, Slot& s) {
     if (cap > bound) cap = bound;
     s.ctab_pool_capacity = (uint32_t)cap;
     CUDA_TRY(cudaMalloc(&s.d_ctab, sizeof(CompactHeader) + n_classes * sizeof(ClassEntry) + cap * sizeof(uint16_t) + 16));
-    CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&s.h_hdr), sizeof(CompactHeader), cudaHostAllocDefault));
+    CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&s.h_hdr), sizeof(CompactHeader), cudaHostAllocMapped));
     memset(s.h_hdr, 0, sizeof(CompactHeader));
+    CUDA_TRY(cudaHostGetDevicePointer(reinterpret_cast<void**>(&s.d_hdr_alias), s.h_hdr, 0));
     CUDA_TRY(cudaMalloc(&s.d_counters, 2 * sizeof(uint32_t)));
+    CUDA_TRY(cudaMemset(s.d_counters, 0, 2 * sizeof(uint32_t)));
   }
   CUDA_TRY(cudaHostAlloc(&s.h_blob, l.total, cudaHostAllocDefault));
   CUDA_TRY(cudaEventCreateWithFlags(&s.ready, cudaEventDisableTiming));
@@ -809,6 +832,7 @@ static int create_impl(lig_ctx* c, int device, int max_pods, int max_adapters, i
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, v));
   CUDA_TRY(cudaFuncSetAttribute(lig_class_build_kernel<false>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, v));
+  CUDA_TRY(cudaFuncSetAttribute(lig_class_build_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v));
   CUDA_TRY(cudaFuncSetAttribute(lig_scan_kernel<true>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, v));
   CUDA_TRY(cudaFuncSetAttribute(lig_scan_kernel<false>,
@@ -840,6 +864,7 @@ static int create_impl(lig_ctx* c, int device, int max_pods, int max_adapters, i
   }
   if (const char* e = getenv("LIG_TMA_BULK_STORE")) c->tma_bulk_store = atoi(e) != 0;
   if (const char* e = getenv("LIG_TAB_SMEM")) c->tab_smem = atoi(e) != 0;
+  if (const char* e = getenv("LIG_FAST_BUILD")) c->fast_build = atoi(e) != 0;
   if (const char* e = getenv("LIG_MODELS_GROUPS")) {
     int v2 = atoi(e);
     if (v2 == 1 || v2 == 2) c->models_groups = v2;

@@ -665,10 +665,14 @@ struct CompactHeader {
   uint32_t reserved;
 };
 struct CompactOut {       // where the build writes the blob; counters[0] = pool cursor of the own
-  unsigned char* blob;    // lists, counters[1] = finished CTAs (both zeroed before the launch)
+  unsigned char* blob;    // lists, counters[1] = finished CTAs (zero at allocation, reset by the sealing CTA)
   uint32_t* counters;
   uint32_t pool_capacity;
+  CompactHeader* host_hdr;   // page-locked, device-mapped copy of the header for the host's launch
+                             // decision: written by the sealing thread, no D2H copy on the stream
+  unsigned long long* dbg;   // LIG_BUILD_DEBUG: clock64() stamps of CTA 0 / thread 0 (nullable)
 };
+#define LIG_STAMP(k) do { if (co.dbg && blockIdx.x == 0 && threadIdx.x == 0) co.dbg[k] = clock64(); } while (0)
 
 template <bool kStaged>
 __global__ void __launch_bounds__(kBuildThreads)
@@ -714,6 +718,14 @@ lig_class_build_kernel(SnapView s, Thr thr, ClassEntry* __restrict__ cls,
         chdr->bytes = total <= co.pool_capacity
                           ? (uint32_t)((sizeof(CompactHeader) + (size_t)n_classes * sizeof(ClassEntry) +
                                         (size_t)total * sizeof(uint16_t) + 15) & ~(size_t)15) : 0u;
+        if (co.host_hdr) {
+          co.host_hdr->n_classes = chdr->n_classes;
+          co.host_hdr->pool_entries = total;
+          co.host_hdr->reserved = 0;
+          co.host_hdr->bytes = chdr->bytes;
+        }
+        co.counters[0] = 0;   // ready for the next build of this slot
+        co.counters[1] = 0;
       }
     }
   };
@@ -886,6 +898,361 @@ lig_class_build_kernel(SnapView s, Thr thr, ClassEntry* __restrict__ cls,
     __syncwarp();
   }
   seal(fixed_entries);
+}
+
+// ---- K2a (fast form): pools of up to 4096 pods ------------------------------------------------------
+// Same tables, bit for bit, as lig_class_build_kernel; the differences are all about latency (the
+// build is a chain of a dozen tiny block-wide stages, so it is bound by synchronisation and
+// dependent shared-memory round trips, not by work):
+//   * the shared stages keep each thread's 8 pods (word warp + 16 j, bit lane) in REGISTERS, sets
+//     are 8-bit masks per thread, a stage is a few compares + one warp reduction + ONE
+//     __syncthreads (double-buffered scratch) instead of ballot passes over shared-memory masks;
+//   * one class per warp (twice the CTAs), its bitmap row requested from HBM/L2 before the shared
+//     stages start, pool space reserved (atomic) before the compaction, one compaction pass that
+//     writes the strided row and the pool entry together, lanes owning contiguous words.
+constexpr int kOwn = 8;                                 // words per warp: W <= kBuildWarps * kOwn
+constexpr int kFastMaxWords = kBuildWarps * kOwn;       // 128 words = 4096 pods
+
+struct FastShared {          // double-buffered scratch of the block-wide stages
+  uint32_t red_u[2][4][kBuildWarps];
+  int red_i[2][4][kBuildWarps];
+  double red_d[2][4][kBuildWarps];
+};
+
+__host__ __device__ inline size_t fast_fixed_bytes(int W) {
+  const size_t b = ((sizeof(FastShared) + 15) & ~(size_t)15) + (size_t)(7 + kBuildWarps) * (size_t)W * sizeof(uint32_t);
+  return (b + 15) & ~(size_t)15;
+}
+
+// Set bits of X (ascending) -> out_a[0..n) and out_b[0..n); lane l owns the contiguous words
+// [l * per, (l + 1) * per): one warp scan for the whole mask.
+__device__ __forceinline__ void compact_mask_to_two_lists(const uint32_t* X, int W, int lane,
+                                                          uint16_t* __restrict__ out_a,
+                                                          uint16_t* __restrict__ out_b, bool write_b) {
+  const int per = (W + 31) / 32;
+  const int w0 = lane * per;
+  uint32_t c = 0;
+  for (int i = 0; i < per; ++i) c += (w0 + i < W) ? __popc(X[w0 + i]) : 0;
+  uint32_t incl = c;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const uint32_t o = __shfl_up_sync(kFull, incl, off);
+    if (lane >= off) incl += o;
+  }
+  uint32_t pos = incl - c;
+  for (int i = 0; i < per; ++i) {
+    if (w0 + i >= W) break;
+    uint32_t bits = X[w0 + i];
+    while (bits) {
+      const int b = __ffs(bits) - 1;
+      bits &= bits - 1;
+      const uint16_t pod = (uint16_t)((w0 + i) * 32 + b);
+      out_a[pos] = pod;
+      if (write_b) out_b[pos] = pod;
+      ++pos;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kBuildThreads)
+lig_class_build_fast_kernel(SnapView s, Thr thr, ClassEntry* __restrict__ cls, uint16_t* __restrict__ lists,
+                            int list_stride, CompactOut co) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int P = s.P, W = s.W, A = s.A;
+  FastShared* sh = reinterpret_cast<FastShared*>(smem);
+  uint32_t* masks = reinterpret_cast<uint32_t*>(smem + ((sizeof(FastShared) + 15) & ~(size_t)15));
+  uint32_t* M_room = masks;            // n_active < max_active                       filter.go:175-177
+  uint32_t* CB = masks + 1 * W;        // critical: mask the adapter row is ANDed with
+  uint32_t* CZ = masks + 2 * W;        // critical mode 1: (least-queuing set) & room
+  uint32_t* SB = masks + 3 * W;        // sheddable: (least-queuing set of S) & ~room
+  uint32_t* SZ = masks + 4 * W;        // sheddable: (least-queuing set of S) & room
+  uint32_t* TMPC = masks + 5 * W;      // the default critical survivor set on its way to a list
+  uint32_t* TMPS = masks + 6 * W;      // the default sheddable one
+  uint32_t* X = masks + (size_t)(7 + warp) * W;   // per-warp scratch
+  const int n_classes = 2 * (A + 1);
+  const uint32_t rc_row = (uint32_t)n_classes * (uint32_t)list_stride;
+  const uint32_t rs_row = rc_row + (uint32_t)list_stride;
+  const uint32_t none = rs_row + (uint32_t)list_stride;
+  CompactHeader* chdr = reinterpret_cast<CompactHeader*>(co.blob);
+  uint4* centries = reinterpret_cast<uint4*>(co.blob + sizeof(CompactHeader));
+  uint16_t* cpool = reinterpret_cast<uint16_t*>(co.blob + sizeof(CompactHeader) + (size_t)n_classes * sizeof(ClassEntry));
+
+  // this warp's first class: ask for its bitmap row now, use it after the shared stages
+  // classes are dealt to the CTAs round-robin: the popular adapters (low ids, long sparse walks)
+  // end up on different SMs instead of sharing one
+  const int c0 = warp * (int)gridDim.x + (int)blockIdx.x;
+  uint32_t rowreg[kFastMaxWords / 32] = {0, 0, 0, 0};
+  {
+    const int a0 = c0 >= A + 1 ? c0 - (A + 1) : c0;
+    if (c0 < n_classes && a0 < A) {
+      const uint32_t* row = s.bitmap + (size_t)a0 * W;
+#pragma unroll
+      for (int i = 0; i < kFastMaxWords / 32; ++i)
+        if (lane + 32 * i < W) rowreg[i] = __ldg(row + lane + 32 * i);
+    }
+  }
+  LIG_STAMP(0);
+  const Fields f = stage_fields(s, smem + fast_fixed_bytes(W));
+  __syncthreads();
+  LIG_STAMP(1);
+
+  // ---- this thread's pods ----
+  int q[kOwn];
+  double kv[kOwn];
+  uint32_t valid = 0, room = 0, low = 0, shed = 0;
+#pragma unroll
+  for (int j = 0; j < kOwn; ++j) {
+    const int w = warp + kBuildWarps * j;
+    const int p = w * 32 + lane;
+    q[j] = 0;
+    kv[j] = 0.0;
+    if (w < W && p < P) {
+      q[j] = f.q[p];
+      kv[j] = f.kv[p];
+      valid |= 1u << j;
+      if (f.na[p] < f.ma[p]) room |= 1u << j;                                       // filter.go:175-177
+      if ((long long)q[j] < thr.q_lora) low |= 1u << j;                             // scheduler.go:58-60
+      if ((long long)q[j] <= thr.q_crit && kv[j] <= thr.kv_thr) shed |= 1u << j;    // scheduler.go:74-79
+    }
+  }
+  int rb = 0;   // which half of the reduction scratch the next block-wide stage uses
+  // Block-wide stages.  The critical and the sheddable side of the tree are independent, so every
+  // stage reduces BOTH at once: 5 barriers for the whole shared part of the tree.
+  auto sum4 = [&](uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t* out) {
+    a = __reduce_add_sync(kFull, a);
+    b = __reduce_add_sync(kFull, b);
+    c = __reduce_add_sync(kFull, c);
+    d = __reduce_add_sync(kFull, d);
+    if (lane == 0) { sh->red_u[rb][0][warp] = a; sh->red_u[rb][1][warp] = b; sh->red_u[rb][2][warp] = c; sh->red_u[rb][3][warp] = d; }
+    __syncthreads();
+    out[0] = out[1] = out[2] = out[3] = 0;
+#pragma unroll
+    for (int i = 0; i < kBuildWarps; ++i) {
+      out[0] += sh->red_u[rb][0][i]; out[1] += sh->red_u[rb][1][i];
+      out[2] += sh->red_u[rb][2][i]; out[3] += sh->red_u[rb][3][i];
+    }
+    rb ^= 1;
+  };
+  auto seal = [&](uint32_t fixed_entries) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      if (atomicAdd(co.counters + 1, 1u) == gridDim.x - 1) {
+        __threadfence();
+        const uint32_t total = fixed_entries + *reinterpret_cast<volatile uint32_t*>(co.counters);
+        chdr->n_classes = (uint32_t)n_classes;
+        chdr->pool_entries = total;
+        chdr->reserved = 0;
+        chdr->bytes = total <= co.pool_capacity
+                          ? (uint32_t)((sizeof(CompactHeader) + (size_t)n_classes * sizeof(ClassEntry) +
+                                        (size_t)total * sizeof(uint16_t) + 15) & ~(size_t)15) : 0u;
+        if (co.host_hdr) {
+          co.host_hdr->n_classes = chdr->n_classes;
+          co.host_hdr->pool_entries = total;
+          co.host_hdr->reserved = 0;
+          co.host_hdr->bytes = chdr->bytes;
+        }
+        co.counters[0] = 0;   // ready for the next build of this slot
+        co.counters[1] = 0;
+      }
+    }
+  };
+
+  // ---- shared stages ----
+  LIG_STAMP(2);
+  uint32_t cnt[4];
+  sum4(__popc(low), __popc(shed), __popc(low & room), 0u, cnt);                       // barrier 1
+  const uint32_t n_low = cnt[0], n_shed = cnt[1], n_low_room = cnt[2];
+  LIG_STAMP(3);
+  // critical side, start set:  low-queue pods that can accept the adapter, else all low-queue pods
+  // (scheduler.go:58-69); no low-queue pod at all: every pod (scheduler.go:71)
+  uint32_t tc = n_low > 0 ? (n_low_room > 0 ? (low & room) : low) : valid;
+  uint32_t n_tc = n_low > 0 ? (n_low_room > 0 ? n_low_room : n_low) : (uint32_t)P;
+  // sheddable side, start set: pods with capacity (scheduler.go:74-79); empty -> drop
+  uint32_t ts = shed;
+  uint32_t n_ts = n_shed;
+  // leastQueuingFilterFunc on both                                             filter.go:102-122
+  {
+    int mnc = 0x7fffffff, mxc = 0, mns = 0x7fffffff, mxs = 0;
+#pragma unroll
+    for (int j = 0; j < kOwn; ++j) {
+      if ((tc >> j) & 1u) { mnc = min(mnc, q[j]); mxc = max(mxc, q[j]); }
+      if ((ts >> j) & 1u) { mns = min(mns, q[j]); mxs = max(mxs, q[j]); }
+    }
+    mnc = __reduce_min_sync(kFull, mnc); mxc = __reduce_max_sync(kFull, mxc);
+    mns = __reduce_min_sync(kFull, mns); mxs = __reduce_max_sync(kFull, mxs);
+    if (lane == 0) { sh->red_i[rb][0][warp] = mnc; sh->red_i[rb][1][warp] = mxc; sh->red_i[rb][2][warp] = mns; sh->red_i[rb][3][warp] = mxs; }
+    __syncthreads();                                                                  // barrier 2
+#pragma unroll
+    for (int i = 0; i < kBuildWarps; ++i) {
+      mnc = min(mnc, sh->red_i[rb][0][i]); mxc = max(mxc, sh->red_i[rb][1][i]);
+      mns = min(mns, sh->red_i[rb][2][i]); mxs = max(mxs, sh->red_i[rb][3][i]);
+    }
+    rb ^= 1;
+    // min + (max - min) / len, Go int64 truncated division (see stage_least_queuing)
+    const long long thc = (long long)mnc + (long long)(((uint32_t)mxc - (uint32_t)mnc) / (n_tc ? n_tc : 1u));
+    const long long ths = (long long)mns + (long long)(((uint32_t)mxs - (uint32_t)mns) / (n_ts ? n_ts : 1u));
+    uint32_t kc = 0, ks = 0;
+#pragma unroll
+    for (int j = 0; j < kOwn; ++j) {
+      if (((tc >> j) & 1u) && (long long)q[j] >= (long long)mnc && (long long)q[j] <= thc) kc |= 1u << j;
+      if (((ts >> j) & 1u) && (long long)q[j] >= (long long)mns && (long long)q[j] <= ths) ks |= 1u << j;
+    }
+    tc = n_tc ? kc : 0u;
+    ts = n_ts ? ks : 0u;
+  }
+  sum4(__popc(tc), __popc(ts), __popc(tc & room), __popc(ts & room), cnt);            // barrier 3
+  n_tc = cnt[0];
+  n_ts = cnt[1];
+  // "low cost LoRA" on the least-queuing set: (affinity | room); for the default lists (no
+  // affinity) that is the room part, falling back to the whole set           scheduler.go:35-46
+  uint32_t cb_set, cz_set = 0, sb_set = 0, sz_set = 0;
+  if (n_low > 0) {
+    cb_set = low;                      // rows are ANDed with the low-queue set ("affinity LoRA")
+  } else {
+    cz_set = tc & room;
+    cb_set = tc & ~room;
+    if (cnt[2] > 0) { tc = cz_set; n_tc = cnt[2]; }
+  }
+  if (n_shed > 0) {
+    sz_set = ts & room;
+    sb_set = ts & ~room;
+    if (cnt[3] > 0) { ts = sz_set; n_ts = cnt[3]; }
+  }
+  // leastKVCacheFilterFunc on both                                             filter.go:134-154
+  {
+    double mnc = 1.7976931348623157e308, mxc = 0.0, mns = 1.7976931348623157e308, mxs = 0.0;
+#pragma unroll
+    for (int j = 0; j < kOwn; ++j) {
+      if ((tc >> j) & 1u) { if (kv[j] <= mnc) mnc = kv[j]; if (kv[j] >= mxc) mxc = kv[j]; }
+      if ((ts >> j) & 1u) { if (kv[j] <= mns) mns = kv[j]; if (kv[j] >= mxs) mxs = kv[j]; }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      double o = __shfl_xor_sync(kFull, mnc, off); if (o < mnc) mnc = o;
+      o = __shfl_xor_sync(kFull, mxc, off);        if (o > mxc) mxc = o;
+      o = __shfl_xor_sync(kFull, mns, off);        if (o < mns) mns = o;
+      o = __shfl_xor_sync(kFull, mxs, off);        if (o > mxs) mxs = o;
+    }
+    if (lane == 0) { sh->red_d[rb][0][warp] = mnc; sh->red_d[rb][1][warp] = mxc; sh->red_d[rb][2][warp] = mns; sh->red_d[rb][3][warp] = mxs; }
+    __syncthreads();                                                                  // barrier 4
+#pragma unroll
+    for (int i = 0; i < kBuildWarps; ++i) {
+      double v = sh->red_d[rb][0][i]; if (v < mnc) mnc = v;
+      v = sh->red_d[rb][1][i];        if (v > mxc) mxc = v;
+      v = sh->red_d[rb][2][i];        if (v < mns) mns = v;
+      v = sh->red_d[rb][3][i];        if (v > mxs) mxs = v;
+    }
+    rb ^= 1;
+    const double thc = __dadd_rn(mnc, __ddiv_rn(__dsub_rn(mxc, mnc), (double)(n_tc ? n_tc : 1u)));
+    const double ths = __dadd_rn(mns, __ddiv_rn(__dsub_rn(mxs, mns), (double)(n_ts ? n_ts : 1u)));
+    uint32_t kc = 0, ks = 0;
+#pragma unroll
+    for (int j = 0; j < kOwn; ++j) {
+      if (((tc >> j) & 1u) && kv[j] >= mnc && kv[j] <= thc) kc |= 1u << j;
+      if (((ts >> j) & 1u) && kv[j] >= mns && kv[j] <= ths) ks |= 1u << j;
+    }
+    tc = n_tc ? kc : 0u;
+    ts = n_ts ? ks : 0u;
+  }
+  sum4(__popc(tc), __popc(ts), 0u, 0u, cnt);                                          // barrier 5
+  const uint32_t rc_n = cnt[0], rs_n = cnt[1];
+  const uint32_t rc_status = rc_n ? LIG_OK : LIG_EMPTY;
+  const uint32_t rs_status = n_shed == 0 ? (uint32_t)LIG_DROP : (rs_n ? (uint32_t)LIG_OK : (uint32_t)LIG_EMPTY);
+  LIG_STAMP(4);
+  // sets -> mask words in shared memory (what the per-class part ANDs the bitmap rows with)
+#pragma unroll
+  for (int j = 0; j < kOwn; ++j) {
+    const int w = warp + kBuildWarps * j;
+    const uint32_t w_room = __ballot_sync(kFull, (room >> j) & 1u), w_cb = __ballot_sync(kFull, (cb_set >> j) & 1u),
+                   w_cz = __ballot_sync(kFull, (cz_set >> j) & 1u), w_sb = __ballot_sync(kFull, (sb_set >> j) & 1u),
+                   w_sz = __ballot_sync(kFull, (sz_set >> j) & 1u), w_tc = __ballot_sync(kFull, (tc >> j) & 1u),
+                   w_ts = __ballot_sync(kFull, (ts >> j) & 1u);
+    if (lane == 0 && w < W) {
+      M_room[w] = w_room; CB[w] = w_cb; CZ[w] = w_cz; SB[w] = w_sb; SZ[w] = w_sz; TMPC[w] = w_tc; TMPS[w] = w_ts;
+    }
+  }
+  __syncthreads();
+  // the two default lists, by the last two warps of CTA 0 (its first warps hold the most popular adapters)
+  if (blockIdx.x == 0 && warp == kBuildWarps - 1 && rc_n) compact_mask_to_two_lists(TMPC, W, lane, lists + rc_row, cpool + 1, true);
+  if (blockIdx.x == 0 && warp == kBuildWarps - 2 && rs_n)
+    compact_mask_to_two_lists(TMPS, W, lane, lists + rs_row, cpool + 1 + rc_n, true);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    cpool[0] = 0xffffu;
+    lists[none] = 0xffffu;
+  }
+  const uint32_t fixed_entries = 1u + rc_n + rs_n;
+  LIG_STAMP(5);
+
+  // ---- per class (one warp each) ----
+  for (int c = c0; c < n_classes; c += gridDim.x * kBuildWarps) {
+    const bool critical = c >= A + 1;
+    const int a = critical ? c - (A + 1) : c;
+    ClassEntry e;
+    uint32_t coff = 0;
+    if (!critical && n_shed == 0) {
+      e = make_entry(0u, (uint32_t)LIG_DROP, none);                        // scheduler.go:83-89
+    } else {
+      const uint32_t* Bm = critical ? CB : SB;
+      const uint32_t* Zm = critical ? (n_low > 0 ? nullptr : CZ) : SZ;
+      uint32_t hit = 0;
+      if (a < A) {
+        if (c != c0) {   // later classes of this warp (A > 1183): fetch the row now
+          const uint32_t* row = s.bitmap + (size_t)a * W;
+#pragma unroll
+          for (int i = 0; i < kFastMaxWords / 32; ++i) rowreg[i] = (lane + 32 * i < W) ? __ldg(row + lane + 32 * i) : 0u;
+        }
+#pragma unroll
+        for (int i = 0; i < kFastMaxWords / 32; ++i) {
+          const int w = lane + 32 * i;
+          if (w < W) {
+            const uint32_t t = Bm[w] & rowreg[i];
+            X[w] = t;
+            hit += __popc(t);
+          }
+        }
+        hit = __reduce_add_sync(kFull, hit);
+      }
+      if (hit == 0) {
+        e = critical ? make_entry(rc_n, rc_status, rc_n ? rc_row : none)
+                     : make_entry(rs_n, rs_status, rs_n ? rs_row : none);
+        coff = critical ? (rc_n ? 1u : 0u) : (rs_n ? 1u + rc_n : 0u);
+      } else {
+        uint32_t n = hit;
+        if (Zm) {   // low cost LoRA: (affinity | room) on the least-queuing set     filter.go:163-166
+          n = 0;
+          for (int w = lane; w < W; w += 32) {
+            const uint32_t t = X[w] | Zm[w];
+            X[w] = t;
+            n += __popc(t);
+          }
+          n = __reduce_add_sync(kFull, n);
+        }
+        __syncwarp();
+        if (critical && n_low > 0)      // "affinity LoRA" succeeded -> queueAndKVCacheFilter
+          n = sparse_least_queuing<true>(f, X, W, lane, n);
+        n = sparse_least_kv<true>(f, X, W, lane, n);
+        const uint32_t off = (uint32_t)c * (uint32_t)list_stride;
+        if (n) {
+          uint32_t at = 0;
+          if (lane == 0) at = atomicAdd(co.counters, n);           // pool space for this list
+          at = __shfl_sync(kFull, at, 0) + fixed_entries;
+          compact_mask_to_two_lists(X, W, lane, lists + off, cpool + at, at + n <= co.pool_capacity);
+          coff = at;
+        }
+        e = make_entry(n, n ? (uint32_t)LIG_OK : (uint32_t)LIG_EMPTY, n ? off : none);
+      }
+    }
+    if (lane == 0) {
+      *reinterpret_cast<uint4*>(cls + c) = make_uint4(e.info, e.magic, e.q_limit, e.list_off);
+      centries[c] = make_uint4(e.info, e.magic, e.q_limit, coff);
+    }
+    __syncwarp();
+  }
+  LIG_STAMP(6);
+  seal(fixed_entries);
+  LIG_STAMP(7);
 }
 
 // ---- snapshot delta ---------------------------------------------------------------------------------

@@ -303,3 +303,67 @@ class StaticProvider:
 
     def AllPodMetrics(self):  # noqa: N802
         return list(self._pods)
+
+
+# ---- the step before Schedule: handlers/request.go:42-56, backend/datastore.go:70-105 ----------------
+# Readable twin of oracle/lig_oracle_models.c (draw parity against Go's seeded source is unpinned,
+# see that file's header; the draw is defined on SplitMix64Source(seed ^ rand_key ^ DRAW_DOMAIN)).
+DRAW_DOMAIN = 0xA0761D6478BD642F
+LIGO_NO_MODEL, LIGO_NO_TARGET = 3, 4
+
+
+@dataclass
+class TargetModel:                      # api/v1alpha1 TargetModel
+    name: str
+    weight: int
+
+
+@dataclass
+class InferenceModel:                   # api/v1alpha1 InferenceModel, the fields the path reads
+    name: str
+    critical: bool = False
+    target_models: List[TargetModel] = field(default_factory=list)
+
+
+def random_weighted_draw(model: InferenceModel, source: SplitMix64Source) -> str:   # datastore.go:78-98
+    weights = 0
+    for tm in model.target_models:
+        weights = _go_int32(weights + tm.weight)
+    if weights <= 0:
+        raise ValueError("invalid argument to Int31n")        # Go panics
+    random_val = source.int31n(weights)                                              # datastore.go:90
+    for tm in model.target_models:                                                   # datastore.go:91-97
+        if random_val < tm.weight:
+            return tm.name
+        random_val -= tm.weight
+    return ""
+
+
+def _go_int32(x: int) -> int:
+    x &= 0xFFFFFFFF
+    return x - (1 << 32) if x >= (1 << 31) else x
+
+
+def resolve(models: Sequence[Optional[InferenceModel]], model_id: int, seed: int, rand_key: int):
+    """request.go:42-56 -> (status, resolved target model name, critical, target index)."""
+    if not (0 <= model_id < len(models)) or models[model_id] is None:                # request.go:42-45
+        return LIGO_NO_MODEL, None, False, 255
+    m = models[model_id]
+    name, idx = m.name, 255
+    if m.target_models:                                                              # request.go:46-51
+        try:
+            name = random_weighted_draw(m, SplitMix64Source(seed ^ rand_key ^ DRAW_DOMAIN))
+        except ValueError:
+            return LIGO_NO_TARGET, None, False, 255
+        if name == "":
+            return LIGO_NO_TARGET, None, False, 255
+        # the index of the FIRST target the loop would stop at (names may repeat)
+        src = SplitMix64Source(seed ^ rand_key ^ DRAW_DOMAIN)
+        rv = src.int31n(sum(t.weight for t in m.target_models))
+        idx = 0
+        for k, tm in enumerate(m.target_models):
+            if rv < tm.weight:
+                idx = k
+                break
+            rv -= tm.weight
+    return LIGO_OK, name, m.critical, idx

@@ -698,3 +698,42 @@ def test_readers_on_many_streams_vs_device_uploads(oracle):
             assert (got["pod_idx"] < P_).all()
     finally:
         e.close()
+
+
+def test_fast_and_general_class_build_agree(monkeypatch):
+    """Pools of up to 4096 pods are built by the register-resident fast kernel, larger ones (or
+    LIG_FAST_BUILD=0) by the general one: every class table and every pick must be identical."""
+    cases = [(WL.make_snapshot(P, A, seed=100 + P).packed, A) for P, A in
+             [(1, 3), (31, 3), (33, 5), (100, 17), (512, 256), (1000, 40), (4095, 64), (4096, 1024)]]
+    pools = [pack_pod_metrics(EDGE_POOLS[k]) for k in ("all_nan_kv", "q_all_high", "drop_all", "ties", "overfull", "int32_extremes")]
+    cases += [(p, p.A) for p in pools]
+    monkeypatch.setenv("LIG_FAST_BUILD", "0")
+    general = Engine(0, max_pods=4096, max_adapters=1024, max_batch=1 << 16)
+    monkeypatch.setenv("LIG_FAST_BUILD", "1")
+    fast = Engine(0, max_pods=4096, max_adapters=1024, max_batch=1 << 16)
+    try:
+        for ep, (packed, A) in enumerate(cases, start=1):
+            general.upload_snapshot(ep, packed)
+            fast.upload_snapshot(ep, packed)
+            reqs = np.concatenate([all_class_requests(A, extra_ids=(-1, A + 3)), WL.make_requests(20000, A, seed=ep)])
+            reqs = np.ascontiguousarray(reqs)
+            assert np.array_equal(general.schedule_batch(ep, 9, reqs), fast.schedule_batch(ep, 9, reqs)), (packed.P, A)
+            step = max(1, (A + 1) // 64)
+            for crit in (False, True):
+                for a in list(range(0, A + 1, step)) + [A]:
+                    g, f_ = general.read_class(ep, crit, a, packed.P), fast.read_class(ep, crit, a, packed.P)
+                    assert g[0] == f_[0] and g[1] == f_[1] and g[2].tolist() == f_[2].tolist(), (packed.P, A, crit, a)
+            # the resident queue kernel reads the COMPACT tables: same answers from both builds
+            import torch
+            d_reqs = torch.from_numpy(reqs.view(np.uint8).reshape(-1)).cuda()
+            outs = []
+            for e in (general, fast):
+                d_out = [torch.zeros(len(reqs) * 8, dtype=torch.uint8, device="cuda") for _ in range(2)]
+                e.schedule_batches_device(ep, 9, [d_reqs.data_ptr()] * 2, len(reqs), [t.data_ptr() for t in d_out], 0)
+                torch.cuda.synchronize()
+                outs.append(d_out[1].cpu().numpy().view(PICK_DTYPE))
+                assert e.pick_kernel_info(ep)["tables_in_smem"]
+            assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], general.schedule_batch(ep, 10, reqs))
+    finally:
+        general.close()
+        fast.close()

@@ -146,3 +146,31 @@ def test_models_batch_equals_resolve_then_schedule(oracle):
             continue
         st, pod, _ = pool.schedule(name, crit, 11, 1000 + i)
         assert (out[i]["status"], out[i]["pod_idx"], out[i]["target_idx"]) == (st, pod if st == 0 else -1, k)
+
+
+def test_c_and_python_restatements_of_the_resolve_step_agree(oracle):
+    """Two independently written restatements (C: lig_oracle_models.c, Python: lig_oracle_py.py) of
+    request.go:42-56 + datastore.go:78-98 give the same draw for random model tables and keys."""
+    from oracle import lig_oracle_py as PY
+    rng = np.random.default_rng(17)
+    for it in range(60):
+        n_models = int(rng.integers(1, 12))
+        recs, py_models = [], []
+        for m in range(n_models):
+            if rng.random() < 0.1:
+                recs.append(None)
+                py_models.append(None)
+                continue
+            nt = int(rng.integers(0, 6))
+            tms = [(f"t{m}-{k}", int(rng.choice([0, 1, 2, 10, 50, 100, 2**20, 2**29]))) for k in range(nt)]
+            recs.append(dict(name=f"m{m}", critical=bool(rng.integers(0, 2)), targets=tms))
+            py_models.append(PY.InferenceModel(f"m{m}", bool(recs[-1]["critical"]), [PY.TargetModel(n, w) for n, w in tms]))
+        mo = oracle.Models(recs)
+        for _ in range(40):
+            m = int(rng.integers(0, n_models + 2))
+            seed, key = int(rng.integers(0, 2**63)), int(rng.integers(0, 2**63))
+            rc_c, name_c, crit_c, k_c = mo.resolve(m, seed, key) if m < n_models else (oracle.LIGO_NO_MODEL, None, False, 255)
+            rc_p, name_p, crit_p, k_p = PY.resolve(py_models, m, seed, key)
+            assert (rc_c, name_c) == (rc_p, name_p), (it, m, recs[m] if m < n_models else None)
+            if rc_c == 0:
+                assert (crit_c, k_c) == (crit_p, k_p)
