@@ -1,7 +1,6 @@
 package gpuscheduling
 
 import (
-	"fmt"
 	"math"
 
 	"inference.networking.x-k8s.io/llm-instance-gateway/pkg/ext-proc/backend"
@@ -20,29 +19,34 @@ type packedSnapshot struct {
 	bitmap     []uint32 // adapter-major, A x ceil(P/32)
 	adapterIDs map[string]int32
 	pods       []backend.Pod
+	excluded   int // pods left out of this snapshot: a metric did not fit the device record
 }
 
 // packSnapshot interns adapter names (order of first appearance) and narrows the Go-width
-// metrics to the device record.  WaitingQueueSize must fit int32 (an out-of-range value is an
-// error, never a silent wrap); MaxActiveModels saturates to [0, 65535], which cannot change
+// metrics to the device record.  A pod whose WaitingQueueSize does not fit int32 or that lists
+// more than 65534 active models cannot be represented: it is LEFT OUT of this snapshot and
+// counted (never a silent wrap, and never a failed tick that would freeze the whole pool on a
+// stale snapshot).  MaxActiveModels saturates to [0, 65535], which cannot change
 // len(ActiveModels) < MaxActiveModels because len(ActiveModels) <= 65534.
-func packSnapshot(all []*backend.PodMetrics) (*packedSnapshot, error) {
+func packSnapshot(in []*backend.PodMetrics) (*packedSnapshot, error) {
+	all := make([]*backend.PodMetrics, 0, len(in))
+	for _, pm := range in {
+		if pm.WaitingQueueSize > math.MaxInt32 || pm.WaitingQueueSize < math.MinInt32 || len(pm.ActiveModels) > 65534 {
+			continue
+		}
+		all = append(all, pm)
+	}
 	P := len(all)
 	W := (P + 31) / 32
 	s := &packedSnapshot{
 		P: P, kv: make([]float64, P), q: make([]int32, P), nActive: make([]uint16, P),
 		maxActive: make([]uint16, P), adapterIDs: map[string]int32{}, pods: make([]backend.Pod, P),
+		excluded: len(in) - len(all),
 	}
 	for i, pm := range all {
 		s.pods[i] = pm.Pod
 		s.kv[i] = pm.KVCacheUsagePercent
-		if pm.WaitingQueueSize > math.MaxInt32 || pm.WaitingQueueSize < math.MinInt32 {
-			return nil, fmt.Errorf("pod %v: WaitingQueueSize %d does not fit the device record", pm.Pod, pm.WaitingQueueSize)
-		}
 		s.q[i] = int32(pm.WaitingQueueSize)
-		if len(pm.ActiveModels) > 65534 {
-			return nil, fmt.Errorf("pod %v: %d active models exceed the device record", pm.Pod, len(pm.ActiveModels))
-		}
 		s.nActive[i] = uint16(len(pm.ActiveModels))
 		switch m := pm.MaxActiveModels; {
 		case m < 0:
