@@ -643,11 +643,34 @@ def main():
     # (b) the 16-byte descriptor call of round 1 (requests resolved on the host).
     e2e_steps = max(3, min(K, 50))
     packed = snap.packed
-    mid_pin = [torch.from_numpy(WL.make_model_requests(R, A, seed=WL.REQUEST_SEED + 77 + b).view(np.uint8)).pin_memory()
-               for b in range(4)]
-    mout_pin = torch.zeros(R * 4, dtype=torch.uint8).pin_memory()
-    req_pin = [torch.from_numpy(hb.view(np.uint8).reshape(-1)).pin_memory() for hb in host_batches[:4]]
-    out_pin = torch.zeros(R * 8, dtype=torch.uint8).pin_memory()
+    # page-locked buffers from the product's own allocator (lig_host_alloc: device-mapped, placed on
+    # the GPU's NUMA node) — what the Go shim hands to its callers as unsafe.Slice
+    import ctypes
+    from llm_instance_gateway_b200 import _native as N
+    lib = N.load()
+
+    class Pinned:
+        def __init__(self, nbytes):
+            self.ptr = lib.lig_host_alloc(nbytes)
+            if not self.ptr:
+                raise SystemExit("lig_host_alloc failed")
+            self.np = np.ctypeslib.as_array((ctypes.c_uint8 * nbytes).from_address(self.ptr))
+
+        def data_ptr(self):
+            return self.ptr
+
+        def numpy(self):
+            return self.np
+
+    def pinned_copy(arr):
+        b = Pinned(arr.nbytes)
+        b.np[:] = arr.view(np.uint8).reshape(-1)
+        return b
+
+    mid_pin = [pinned_copy(WL.make_model_requests(R, A, seed=WL.REQUEST_SEED + 77 + b)) for b in range(4)]
+    mout_pin = Pinned(R * 4)
+    req_pin = [pinned_copy(hb) for hb in host_batches[:4]]
+    out_pin = Pinned(R * 8)
     ep2 = scratch
 
     def e2e_models(i, refresh):
@@ -679,7 +702,7 @@ def main():
     e2e_descr_resident = e2e_rate(e2e_descr, False)
     # the e2e result is a real answer: compare the last model-request step with the oracle
     want_last = mo.schedule_batch(pool, np.ascontiguousarray(
-        np.frombuffer(mid_pin[(e2e_steps - 1) % 4].numpy(), dtype=np.uint32)[:parity_port]), 100 + e2e_steps - 1, 0)
+        mid_pin[(e2e_steps - 1) % 4].numpy().view(np.uint32)[:parity_port]), 100 + e2e_steps - 1, 0)
     if not np.array_equal(mout_pin.numpy().view(MPICK_DTYPE)[:parity_port], want_last):
         raise SystemExit("e2e result differs from the oracle")
     clocks = sampler.stop() if rank == 0 else None

@@ -5,8 +5,11 @@
 // CPU implementation of the scheduling path in this library: if CUDA is missing every entry point
 // fails with LIG_ERR_CUDA.
 #include <cuda_runtime.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 
 #include <atomic>
+#include <cctype>
 #include <cstdarg>
 #include <cstddef>
 #include <cstdio>
@@ -550,6 +553,37 @@ int check_shape(const lig_ctx* c, int P, int A) {
     return fail(LIG_ERR_INVALID, "A=%d outside [0, max_adapters=%d]", A, c->max_adapters);
   return 0;
 }
+
+// Scoped "allocate on the GPU's NUMA node" memory policy for the calling thread.
+struct NumaBind {
+  bool active = false;
+  NumaBind() {
+    const char* env = getenv("LIG_NUMA");
+    if (env && atoi(env) == 0) return;
+    int dev = 0;
+    char bus[32] = "";
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetPCIBusId(bus, sizeof(bus), dev) != cudaSuccess) {
+      cudaGetLastError();
+      return;
+    }
+    for (char* q = bus; *q; ++q) *q = (char)tolower((unsigned char)*q);
+    char path[128];
+    snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bus);
+    FILE* f = fopen(path, "r");
+    if (!f) return;
+    int node = -1;
+    if (fscanf(f, "%d", &node) != 1) node = -1;
+    fclose(f);
+    if (node < 0 || node >= 1024) return;
+    unsigned long mask[16] = {0};
+    mask[node / (8 * sizeof(unsigned long))] |= 1ul << (node % (8 * sizeof(unsigned long)));
+    // MPOL_PREFERRED = 1: fall back to other nodes rather than fail when the node is full
+    active = syscall(SYS_set_mempolicy, 1, mask, sizeof(mask) * 8) == 0;
+  }
+  ~NumaBind() {
+    if (active) syscall(SYS_set_mempolicy, 0 /* MPOL_DEFAULT */, nullptr, 0);
+  }
+};
 
 // Ranges handed out by lig_host_alloc (and the ctx's own staging buffers): known to be pinned and
 // device-mapped, so the per-call driver query below can be skipped for them.
@@ -1658,6 +1692,10 @@ int lig_read_class(lig_ctx* c, uint64_t epoch, int critical, int adapter_id, int
 void* lig_host_alloc(size_t bytes) {
   void* p = nullptr;
   if (bytes == 0) bytes = 16;
+  // Place the pages on the NUMA node the current CUDA device hangs off: the pick kernel reads and
+  // writes these buffers over PCIe in place, and a remote node adds an inter-socket hop to every
+  // transaction.  Best effort (a sandbox may refuse set_mempolicy): LIG_NUMA=0 turns it off.
+  NumaBind bind;
   cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocMapped | cudaHostAllocPortable);
   if (e != cudaSuccess) {
     cudaGetLastError();
