@@ -421,6 +421,7 @@ def main():
         return d_in, d_out
 
     d_reqs, d_out = resident_ring(host_batches, nb)
+    torch.cuda.synchronize()         # built on torch's default stream; everything below runs on `stream`
     req_ptrs = [t.data_ptr() for t in d_reqs]
     out_ptrs = [t.data_ptr() for t in d_out]
 
@@ -450,6 +451,7 @@ def main():
     model_ids0 = WL.make_model_requests(R, A, seed=WL.REQUEST_SEED + 1000 * rank)
     d_mid = torch.from_numpy(model_ids0.view(np.uint8)).to(dev)
     d_mout = torch.zeros(R * 4, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()     # the fills / copies above ran on torch's default stream, not on `stream`
     with torch.cuda.stream(stream):
         eng.schedule_models_batches_device(epoch, 321, 0, [d_mid.data_ptr()], R, [d_mout.data_ptr()], stream.cuda_stream)
     stream.synchronize()
@@ -572,6 +574,7 @@ def main():
             h["adapter_id"] = rng.integers(0, A + 1, len(h)).astype(np.int32)
         u_in, u_out = resident_ring(uni, nb)
         urp, uop = [t.data_ptr() for t in u_in], [t.data_ptr() for t in u_out]
+        torch.cuda.synchronize()
         with torch.cuda.stream(stream):
             launch_steps(0, K, 5, urp, uop)
         med, _, _, _ = time_regions(lambda r: launch_steps(r * K, K, 5000 + r, urp, uop), K, 0.2, 400)
@@ -584,6 +587,7 @@ def main():
         m_in = [torch.from_numpy(np.roll(mids[b % 2], b * 7919).view(np.uint8)).to(dev) for b in range(nbm)]
         m_out = [torch.zeros(R * 4, dtype=torch.uint8, device=dev) for _ in range(nbm)]
         mip, mop = [t.data_ptr() for t in m_in], [t.data_ptr() for t in m_out]
+        torch.cuda.synchronize()     # (fills ran on torch's default stream)
 
         def launch_models(first, count, seed0):
             idx = [(first + i) % nbm for i in range(count)]
@@ -600,6 +604,7 @@ def main():
         # opt-in in-batch load feedback: how hard does one 2^20-request batch herd onto single pods?
         hist = torch.zeros(P, dtype=torch.int32, device=dev)
         fb_out = torch.zeros(R * 8, dtype=torch.uint8, device=dev)
+        torch.cuda.synchronize()
         S_fb = 65536
         n_win = -(-R // S_fb)            # every rank schedules R requests: the same number of windows
         with torch.cuda.stream(stream):

@@ -41,6 +41,7 @@ def test_gpu_feedback_matches_the_sequential_definition(cfg, R, S, oracle):
         d_reqs = torch.from_numpy(reqs.view(np.uint8).reshape(-1)).cuda()
         d_out = torch.zeros(R * 8, dtype=torch.uint8, device="cuda")
         d_hist = torch.full((c["P"],), -1, dtype=torch.int32, device="cuda")
+        torch.cuda.synchronize()   # the fills / copy ran on torch's default stream
         stream = torch.cuda.Stream()
         for rep in range(2):                      # the scratch copy is rebuilt from the resident epoch every call
             with torch.cuda.stream(stream):

@@ -88,6 +88,7 @@ def test_models_device_queue_matches_host_call(env, oracle, monkeypatch):
             host = [WL.make_model_requests(R, c["A"], seed=30 + b) for b in range(nb)]
             d_ids = [torch.from_numpy(h.view(np.uint8)).cuda() for h in host]
             d_out = [torch.zeros(R * 4, dtype=torch.uint8, device="cuda") for _ in range(nb)]
+            torch.cuda.synchronize()   # the fills / copies ran on torch's default stream
             with torch.cuda.stream(stream):
                 e.schedule_models_batches_device(1, 40, 1 << 33, [t.data_ptr() for t in d_ids], R,
                                                  [t.data_ptr() for t in d_out], stream.cuda_stream)

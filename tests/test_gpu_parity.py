@@ -390,6 +390,7 @@ def test_device_pointer_api_matches_host_api(engine):
     want = engine.schedule_batch(ep, 77, reqs)
     d_reqs = torch.from_numpy(reqs.view(np.uint8).reshape(-1)).cuda()
     d_out = torch.zeros(R * 8, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()   # fills / copies above ran on torch's default stream
     stream = torch.cuda.Stream()
     with torch.cuda.stream(stream):
         engine.schedule_batch_device(ep, 77, d_reqs.data_ptr(), R, d_out.data_ptr(), stream.cuda_stream)
@@ -476,6 +477,7 @@ def test_batch_queue_modes_match_single_batches(mode, monkeypatch):
         host = [WL.make_requests(R, c["A"], seed=100 + b) for b in range(nb)]
         d_reqs = [torch.from_numpy(h.view(np.uint8).reshape(-1)).cuda() for h in host]
         d_out = [torch.zeros(R * 8, dtype=torch.uint8, device="cuda") for _ in range(nb)]
+        torch.cuda.synchronize()   # the fills / copies ran on torch's default stream
         stream = torch.cuda.Stream()
         ep = next_epoch()
         engine.upload_snapshot(ep, snap.packed)
@@ -515,6 +517,7 @@ def test_batch_queue_modes_match_single_batches(mode, monkeypatch):
         assert np.array_equal(d_out[2].cpu().numpy().view(PICK_DTYPE), engine.schedule_batch(ep3, 9, host[2]))
         # pick buffers that are only 8-byte aligned (the ABI's minimum): no TMA bulk store possible
         odd = [torch.zeros(R * 8 + 8, dtype=torch.uint8, device="cuda") for _ in range(3)]
+        torch.cuda.synchronize()   # the fills ran on torch's default stream
         with torch.cuda.stream(stream):
             engine.schedule_batches_device(ep3, 21, [t.data_ptr() for t in d_reqs[:3]], R,
                                            [t.data_ptr() + 8 for t in odd], stream.cuda_stream)
@@ -525,6 +528,7 @@ def test_batch_queue_modes_match_single_batches(mode, monkeypatch):
         nq, Rq = 130, 3000
         big_in = torch.cat([d_reqs[b % nb][: Rq * 16] for b in range(nq)])
         big_out = torch.zeros(nq * Rq * 8, dtype=torch.uint8, device="cuda")
+        torch.cuda.synchronize()
         with torch.cuda.stream(stream):
             engine.schedule_batches_device(ep3, 1000, [big_in.data_ptr() + b * Rq * 16 for b in range(nq)], Rq,
                                            [big_out.data_ptr() + b * Rq * 8 for b in range(nq)], stream.cuda_stream)
@@ -674,6 +678,7 @@ def test_readers_on_many_streams_vs_device_uploads(oracle):
         streams = [torch.cuda.Stream() for _ in range(5)]
         up = torch.cuda.Stream()
         outs = [torch.zeros(R_ * 8, dtype=torch.uint8, device="cuda") for _ in range(5 * 6)]
+        torch.cuda.synchronize()   # the fills ran on torch's default stream
         expect = []
         ep = 200
         e.upload_snapshot_device(ep, P_, A_, blobs[0].data_ptr(), up.cuda_stream)

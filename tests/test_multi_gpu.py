@@ -119,6 +119,7 @@ def _comm_worker(rank, world, id_path, out_dir):
     n_windows = max((R * (r + 1) // world - R * r // world + S_FB - 1) // S_FB for r in range(world))
     d_fb = torch.zeros((hi - lo) * 8, dtype=torch.uint8, device="cuda")
     d_hist = torch.zeros(P, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
     with torch.cuda.stream(stream):
         eng.schedule_batch_feedback_device(5, SEED, d_reqs.data_ptr(), hi - lo, d_fb.data_ptr(), S_FB, n_windows,
                                            d_hist.data_ptr(), stream.cuda_stream)
