@@ -1737,22 +1737,12 @@ __device__ __forceinline__ uint32_t pack_mpick(int pod, uint32_t status, uint32_
   return ((uint32_t)pod & 0xffffu) | (status << 16) | (target << 24);
 }
 
-// resolve: model id -> (adapter, critical, target index); false = LIG_NO_MODEL.
+// The weighted draw of a model with >= 2 targets (entry e): randomVal = r.Int31n(total), then the
+// first k with randomVal < cum[k]                                                datastore.go:81-97
 template <bool kSmem>
-__device__ __forceinline__ bool resolve_model(uint32_t m, const ModelTables& mt, uint64_t seed, uint64_t key,
-                                              uint32_t* adapter, uint32_t* critical, uint32_t* target) {
-  *adapter = 0xffffffffu; *critical = 0; *target = 255u;
-  if (m >= mt.n_models) return false;
-  const uint4 e = kSmem ? mt.entries[m] : __ldg(mt.entries + m);
-  if (!(e.x & kModelPresent)) return false;
-  *critical = (e.x >> 8) & 1u;
+__device__ __forceinline__ void draw_target(const uint4 e, const ModelTables& mt, uint64_t seed, uint64_t key,
+                                            uint32_t* adapter, uint32_t* target) {
   const uint32_t nt = e.x & 0xffu;
-  if (nt <= 1u) {                      // no TargetModels, or a single one: nothing to draw
-    *adapter = e.w;
-    *target = nt ? 0u : 255u;
-    return true;
-  }
-  // randomVal = r.Int31n(weights)                                           datastore.go:90
   const uint32_t total = e.z, shift = (e.x >> 12) & 31u;
   const uint32_t q_limit = total > 1u ? 0x80000000u / total : 1u;
   uint64_t state = seed ^ key ^ LIG_DRAW_DOMAIN;
@@ -1771,6 +1761,24 @@ __device__ __forceinline__ bool resolve_model(uint32_t m, const ModelTables& mt,
   }
   *adapter = tr.x;
   *target = k;
+}
+
+// resolve: model id -> (adapter, critical, target index); false = LIG_NO_MODEL.
+template <bool kSmem>
+__device__ __forceinline__ bool resolve_model(uint32_t m, const ModelTables& mt, uint64_t seed, uint64_t key,
+                                              uint32_t* adapter, uint32_t* critical, uint32_t* target) {
+  *adapter = 0xffffffffu; *critical = 0; *target = 255u;
+  if (m >= mt.n_models) return false;
+  const uint4 e = kSmem ? mt.entries[m] : __ldg(mt.entries + m);
+  if (!(e.x & kModelPresent)) return false;
+  *critical = (e.x >> 8) & 1u;
+  const uint32_t nt = e.x & 0xffu;
+  if (nt <= 1u) {                      // no TargetModels, or a single one: nothing to draw
+    *adapter = e.w;
+    *target = nt ? 0u : 255u;
+    return true;
+  }
+  draw_target<kSmem>(e, mt, seed, key, adapter, target);
   return true;
 }
 
@@ -1822,7 +1830,7 @@ __host__ __device__ constexpr size_t mpersist_smem_bytes(int stages, bool tab_sm
 // groups, tables in shared memory), 4 KB tiles, every thread takes 4 consecutive requests
 // (one LDS.128 in, one 16-byte store out).
 template <int kGroups, int kStages, bool kTabSmem>
-__global__ void __launch_bounds__(persist_threads(kGroups), 2 / kGroups > 0 ? 2 / kGroups : 1)
+__global__ void __launch_bounds__(persist_threads(kGroups), kGroups == 1 ? 3 : 2)
 lig_pick_models_kernel(const __grid_constant__ MQueueParams qp, const uint4* __restrict__ cls,
                        const uint16_t* __restrict__ lists, int A,
                        const unsigned char* __restrict__ ctab, uint32_t ctab_bytes,
@@ -1905,11 +1913,46 @@ lig_pick_models_kernel(const __grid_constant__ MQueueParams qp, const uint4* __r
     while (stage >= kStages) { stage -= kStages; phase ^= 1u; }
     const int i0 = tid * 4;
     const uint64_t key0 = it.first_index + (uint64_t)t * kTile + (uint64_t)i0;
-    uint4 o;
-    o.x = pick_model<kTabSmem>(ids.x, key0 + 0, mt, tab, pool, (uint32_t)A, it.seed);
-    o.y = pick_model<kTabSmem>(ids.y, key0 + 1, mt, tab, pool, (uint32_t)A, it.seed);
-    o.z = pick_model<kTabSmem>(ids.z, key0 + 2, mt, tab, pool, (uint32_t)A, it.seed);
-    o.w = pick_model<kTabSmem>(ids.w, key0 + 3, mt, tab, pool, (uint32_t)A, it.seed);
+    // The thread's 4 requests in three passes.  (1) entry lookups; models with at most one target
+    // are resolved on the spot.  (2) the weighted draws: few requests need one (only models that
+    // split traffic), so instead of a divergent branch inside each of the 4 requests every lane
+    // works off its OWN pending requests — the warp runs the draw max-over-lanes(pending) times
+    // (1-2) rather than 4.  (3) the 4 picks.
+    const uint32_t m[4] = {ids.x, ids.y, ids.z, ids.w};
+    uint32_t adapter[4], tgt[4];
+    uint32_t crit = 0, okm = 0, pending = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const bool in_range = m[j] < mt.n_models;
+      const uint4 e = in_range ? (kTabSmem ? mt.entries[m[j]] : __ldg(mt.entries + m[j])) : make_uint4(0, 0, 0, 0);
+      const uint32_t nt = e.x & 0xffu;
+      const bool ok = (e.x & kModelPresent) != 0;
+      okm |= (ok ? 1u : 0u) << j;
+      crit |= ((e.x >> 8) & 1u) << j;
+      adapter[j] = e.w;
+      tgt[j] = nt ? 0u : 255u;
+      pending |= ((ok && nt >= 2u) ? 1u : 0u) << j;
+    }
+    while (pending) {
+      const int j = __ffs((int)pending) - 1;
+      pending &= pending - 1u;
+      const uint32_t mj = j == 0 ? m[0] : j == 1 ? m[1] : j == 2 ? m[2] : m[3];
+      const uint4 e = kTabSmem ? mt.entries[mj] : __ldg(mt.entries + mj);
+      uint32_t a, k;
+      draw_target<kTabSmem>(e, mt, it.seed, key0 + (uint64_t)j, &a, &k);
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj)
+        if (jj == j) { adapter[jj] = a; tgt[jj] = k; }
+    }
+    uint32_t ov[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint64_t key = key0 + (uint64_t)j;
+      const int4 r = make_int4((int)adapter[j], (int)((crit >> j) & 1u), (int)(uint32_t)key, (int)(uint32_t)(key >> 32));
+      const int2 p = kTabSmem ? pick_one_smem(r, tab, pool, (uint32_t)A, it.seed) : pick_one(r, tab, pool, (uint32_t)A, it.seed);
+      ov[j] = ((okm >> j) & 1u) ? pack_mpick(p.x, (uint32_t)p.y & 3u, tgt[j]) : pack_mpick(-1, (uint32_t)LIG_NO_MODEL, 255u);
+    }
+    uint4 o = make_uint4(ov[0], ov[1], ov[2], ov[3]);
     uint32_t* dst = it.out + (size_t)t * kTile + i0;
     if (i0 + 4 <= n) {
       asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1, %2, %3, %4};"
