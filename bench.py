@@ -468,21 +468,21 @@ def main():
               "port_sample_per_rank": int(parity_port), "model_requests_port_sample_per_rank": int(parity_port)}
 
     # --- device-resident throughput ---------------------------------------------------------------
-    def gate():
+    def gate(cycles=100_000):
         """~50 us spin kernel enqueued BEFORE the start event: while it runs the host enqueues the
         start event and all K steps, so the timed region holds device work only, not the host's
         submission latency (the region is still bracketed by barrier + synchronize)."""
-        torch.cuda._sleep(100_000)
+        torch.cuda._sleep(cycles)
 
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
-    def time_regions(fn, Kn, min_seconds, max_reps=2000):
+    def time_regions(fn, Kn, min_seconds, max_reps=2000, gate_cycles=100_000):
         """fn(rep) enqueues one Kn-step region; returns (median ms, min ms, max ms, reps)."""
         times, spent, reps = [], 0.0, 0
         while True:
             barrier()
             with torch.cuda.stream(stream):
-                gate()
+                gate(gate_cycles)
                 ev0.record(stream)
                 fn(reps)
                 ev1.record(stream)
@@ -561,7 +561,10 @@ def main():
         for i in range(3):
             with torch.cuda.stream(stream):
                 upload_tick(scratch)
-        med, _, _, _ = time_regions(lambda r: [upload_tick(scratch) for i in range(10)], 10, 0.05, 50)
+        # (a 1 ms gate: ten ticks are ~60 API calls, which the host must have enqueued before the
+        # device starts on them, or the figure is the host's submission rate)
+        med, _, _, _ = time_regions(lambda r: [upload_tick(scratch) for i in range(10)], 10, 0.05, 50,
+                                    gate_cycles=2_000_000)
         extras["snapshot_tick"] = {"us": med * 1e3 / 10, "n_gpus": world,
                                    "what": ("ncclBroadcast (in the library) + class-table build + compaction" if world > 1
                                             else "device-to-device copy + class-table build + compaction"),

@@ -27,7 +27,7 @@ for cfg in ("C4", "C5"):
         e.upload_snapshot_device(2, c["P"], c["A"], blob.data_ptr(), st.cuda_stream)
     st.synchronize()
     with torch.cuda.stream(st):
-        torch.cuda._sleep(200_000)
+        torch.cuda._sleep(4_000_000)     # ~2 ms: all 20 ticks are enqueued before the device starts
         ev0.record(st)
         for _ in range(20):
             e.upload_snapshot_device(2, c["P"], c["A"], blob.data_ptr(), st.cuda_stream)
