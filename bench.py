@@ -259,6 +259,7 @@ def streaming_leg(device, rate=1e5, seconds=10.0, threads=0, window_us=2):
         lat, nerr = sched.stream_bench(rate, seconds, threads, models, critical, seed=5)
         svc = sched.last_service_latency_us
         st = sched.stats()
+        ft = sched.flush_timing()
     finally:
         sched.close()
         prov.close()
@@ -276,7 +277,11 @@ def streaming_leg(device, rate=1e5, seconds=10.0, threads=0, window_us=2):
             "errors": int(nerr), "caller_threads": threads, "batch_window_us": window_us,
             "batcher": "busy-polling thread, callers spin 100 us before blocking",
             "batches": st["batches"], "avg_batch": st["scheduled"] / max(st["batches"], 1),
-            "snapshot_refreshes": st["refreshes"], "failed_refreshes": st.get("failed_refreshes", 0)}
+            "snapshot_refreshes": st["refreshes"], "failed_refreshes": st.get("failed_refreshes", 0),
+            "slowest_device_call_us": ft["max_device_call_us"], "slowest_flush_us": ft["max_flush_us"],
+            "slowest_call_batch": ft["slowest_call_batch"], "slowest_call_cpu_us": ft["slowest_call_cpu_us"],
+            "tail_note": "max latency vs slowest_device_call_us tells a stalled launch+synchronise (driver / GPU) from a "
+                         "descheduled host thread"}
 
 
 def run_reference(args, cfg, R):

@@ -1,6 +1,7 @@
 // lig_host.cpp — see lig_host.hpp.  Talks to the device only through the C ABI of include/lig.h.
 #include "lig_host.hpp"
 
+#include <time.h>
 #include <algorithm>
 #include <climits>
 #include <cstdio>
@@ -326,6 +327,13 @@ void Scheduler::BatcherLoop() {
 
 void Scheduler::Flush(std::vector<Waiter*>& batch) {
   size_t done = 0;
+  const auto flush_t0 = std::chrono::steady_clock::now();
+  double device_us = 0, device_cpu_us = 0;
+  auto thread_cpu_us = [] {
+    timespec ts;
+    clock_gettime(CLOCK_THREAD_CPUTIME_ID, &ts);
+    return (double)ts.tv_sec * 1e6 + (double)ts.tv_nsec * 1e-3;
+  };
   while (done < batch.size()) {
     const int n = (int)std::min(batch.size() - done, (size_t)opt_.max_batch);
     std::shared_ptr<const Snapshot> snap;
@@ -345,10 +353,17 @@ void Scheduler::Flush(std::vector<Waiter*>& batch) {
         h_reqs_[i].flags = r.Critical ? LIG_REQ_CRITICAL : 0u;
         h_reqs_[i].rand_key = splitmix_next(rng_state_);
       }
+      const auto call_t0 = std::chrono::steady_clock::now();
+      const double cpu_t0 = thread_cpu_us();
       rc = group_ ? lig_group_schedule_batch(group_, snap->epoch, seed_, h_reqs_, n, h_picks_)
            : (opt_.use_doorbell && n <= lig_stream_capacity())
                ? lig_stream_submit(ctx_, snap->epoch, seed_, h_reqs_, n, h_picks_)
                : lig_schedule_batch(ctx_, snap->epoch, seed_, h_reqs_, n, h_picks_);
+      const double call_us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - call_t0).count();
+      if (call_us > device_us) {
+        device_us = call_us;
+        device_cpu_us = thread_cpu_us() - cpu_t0;
+      }
       if (rc != LIG_ERR_STALE_EPOCH) break;   // two refreshes raced past this batch: re-resolve
       std::lock_guard<std::mutex> sk(stats_mu_);
       stats_.stale_retries++;
@@ -383,6 +398,14 @@ void Scheduler::Flush(std::vector<Waiter*>& batch) {
     }
     done += (size_t)n;
   }
+  const double flush_us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - flush_t0).count();
+  std::lock_guard<std::mutex> sk(stats_mu_);
+  if (device_us > stats_.max_device_call_us) {
+    stats_.max_device_call_us = device_us;
+    stats_.slowest_call_cpu_us = device_cpu_us;
+    stats_.slowest_call_batch = stats_.batches ? stats_.batches - 1 : 0;
+  }
+  stats_.max_flush_us = std::max(stats_.max_flush_us, flush_us);
 }
 
 Status Scheduler::ScheduleModel(backend::ModelDataStore& datastore, const std::string& model,

@@ -150,6 +150,11 @@ struct Stats {
   uint64_t excluded_pods = 0;      // pods left out of the last snapshot: a metric did not fit the device record
   double last_pack_us = 0;     // last Refresh: provider slice -> columns + bitmap (host)
   double last_upload_us = 0;   // last Refresh: lig_upload_snapshot (H2D + class tables)
+  double max_device_call_us = 0;   // slowest single lig_schedule_batch call (launch + kernel + synchronise)
+  double max_flush_us = 0;         // slowest Flush: resolve + device call + waking the callers
+  uint64_t slowest_call_batch = 0; // which batch (0-based count of device calls) that slowest call was
+  double slowest_call_cpu_us = 0;  // CPU time the batcher thread burnt inside that call: ~ its wall time when it
+                                   // was spinning on a busy device, far less when the thread itself was descheduled
 };
 
 class Scheduler {

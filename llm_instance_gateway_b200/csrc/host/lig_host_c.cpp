@@ -201,6 +201,14 @@ void ligh_refresh_timing(ligh_scheduler* s, double out[2]) {
   out[1] = st.last_upload_us;
 }
 
+void ligh_flush_timing(ligh_scheduler* s, double out[4]) {
+  scheduling::Stats st = s->sched->stats();
+  out[0] = st.max_device_call_us;
+  out[1] = st.max_flush_us;
+  out[2] = (double)st.slowest_call_batch;
+  out[3] = st.slowest_call_cpu_us;
+}
+
 int ligh_schedule_concurrent(ligh_scheduler* s, int n_threads, int per_thread,
                              const char* const* models, const int* critical, int n_models,
                              int* out_codes, int* out_pod) {

@@ -47,6 +47,7 @@ int ligh_schedule_model(ligh_scheduler*, ligh_datastore*, const char* model, cha
                         char* name, int name_cap, char* addr, int addr_cap, char* err, int err_cap);
 void ligh_stats(ligh_scheduler*, uint64_t out[9]); /* scheduled, batches, max_batch, refreshes, stale_retries */
 void ligh_refresh_timing(ligh_scheduler*, double out[2]); /* last Refresh: host pack us, lig_upload_snapshot us */
+void ligh_flush_timing(ligh_scheduler*, double out[4]);   /* slowest device call us, slowest Flush us, index of that call, thread CPU us inside it */
 
 /* n_threads caller threads each issue `per_thread` blocking Schedule calls (model i of the
  * request table, round-robin); out_codes/out_pod (n_threads*per_thread) receive the code and the

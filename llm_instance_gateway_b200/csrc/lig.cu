@@ -969,6 +969,30 @@ static int create_impl(lig_ctx* c, int device, int max_pods, int max_adapters, i
   CUDA_TRY(cudaHostAlloc(&c->h_out, (size_t)max_batch * sizeof(lig_pick), cudaHostAllocMapped | cudaHostAllocPortable));
   register_pinned(c->h_reqs, (size_t)max_batch * sizeof(lig_req));
   register_pinned(c->h_out, (size_t)max_batch * sizeof(lig_pick));
+  // Nothing on the serving path may allocate or load code: a cudaMalloc in a refresh tick, or the
+  // lazy load of a kernel at its first launch, stalls every concurrent launch of the process for
+  // a millisecond or more (seen as the once-per-run latency outlier of the streaming config).
+  // (a) delta staging for a quarter of the pods with 64 adapters each; larger deltas still grow it
+  {
+    const size_t cap = std::max<size_t>((size_t)64 << 10, (size_t)max_pods / 4 * (24 + 64 * 4) + 4096);
+    CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&c->h_delta), cap, cudaHostAllocDefault));
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->d_delta), cap));
+    c->delta_capacity = cap;
+  }
+  // (b) every kernel a tick or a batch can launch is loaded now
+  {
+    cudaFuncAttributes fa;
+    const void* fns[] = {
+        (const void*)lig_pick_stream_kernel<1>,  (const void*)lig_pick_stream_kernel<2>,
+        (const void*)lig_pick_stream_kernel<4>,  (const void*)lig_pick_stream_kernel<8>,
+        (const void*)lig_pick_stream_kernel<16>, (const void*)lig_pick_queue_kernel<1>,
+        (const void*)lig_pick_queue_kernel<2>,   (const void*)lig_pick_queue_kernel<4>,
+        (const void*)lig_pick_queue_kernel<8>,   (const void*)lig_pick_queue_kernel<16>,
+        (const void*)lig_pick_models_stream_kernel, (const void*)lig_apply_delta_kernel,
+        (const void*)lig_pick_hist_kernel,       (const void*)lig_apply_feedback_kernel,
+    };
+    for (const void* fn : fns) CUDA_TRY(cudaFuncGetAttributes(&fa, fn));
+  }
   return 0;
 }
 

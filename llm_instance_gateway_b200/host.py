@@ -24,7 +24,7 @@ EXPORTED_SYMBOLS = (
     "ligh_provider_new", "ligh_provider_free", "ligh_provider_set_pods", "ligh_scheduler_new",
     "ligh_scheduler_new2",
     "ligh_scheduler_free", "ligh_schedule", "ligh_refresh", "ligh_stats",
-    "ligh_schedule_concurrent", "ligh_stream_bench", "ligh_refresh_timing",
+    "ligh_schedule_concurrent", "ligh_stream_bench", "ligh_refresh_timing", "ligh_flush_timing",
     "ligh_scheduler_new_devices", "ligh_datastore_new", "ligh_datastore_free", "ligh_datastore_set_model",
     "ligh_schedule_model",
 )
@@ -65,6 +65,8 @@ def load() -> C.CDLL:
     lib.ligh_stats.restype = None
     lib.ligh_refresh_timing.argtypes = [vp, vp]
     lib.ligh_refresh_timing.restype = None
+    lib.ligh_flush_timing.argtypes = [vp, vp]
+    lib.ligh_flush_timing.restype = None
     lib.ligh_schedule_concurrent.argtypes = [vp, i32, i32, cpp, vp, i32, vp, vp]
     lib.ligh_stream_bench.argtypes = [vp, C.c_double, C.c_double, i32, cpp, vp, i32, u64, vp, vp, i32,
                                       C.POINTER(i32), C.POINTER(i32)]
@@ -174,6 +176,13 @@ class HostScheduler:
         out = (C.c_double * 2)()
         self._lib.ligh_refresh_timing(self._s, out)
         return {"pack_us": float(out[0]), "upload_us": float(out[1])}
+
+    def flush_timing(self) -> dict:
+        """Slowest single device call and slowest Flush (resolve + call + wake) since creation, us."""
+        out = (C.c_double * 4)()
+        self._lib.ligh_flush_timing(self._s, out)
+        return {"max_device_call_us": float(out[0]), "max_flush_us": float(out[1]), "slowest_call_batch": int(out[2]),
+                "slowest_call_cpu_us": float(out[3])}
 
     def schedule_concurrent(self, n_threads: int, per_thread: int, models: Sequence[str],
                             critical: Sequence[bool]):
