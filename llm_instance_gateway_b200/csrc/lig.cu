@@ -557,6 +557,8 @@ int check_shape(const lig_ctx* c, int P, int A) {
 // Scoped "allocate on the GPU's NUMA node" memory policy for the calling thread.
 struct NumaBind {
   bool active = false;
+  int old_mode = 0;
+  unsigned long old_mask[16] = {0};
   NumaBind() {
     const char* env = getenv("LIG_NUMA");
     if (env && atoi(env) == 0) return;
@@ -577,11 +579,17 @@ struct NumaBind {
     if (node < 0 || node >= 1024) return;
     unsigned long mask[16] = {0};
     mask[node / (8 * sizeof(unsigned long))] |= 1ul << (node % (8 * sizeof(unsigned long)));
+    // the calling thread's own policy (numactl, an embedding runtime) is put back afterwards
+    if (syscall(SYS_get_mempolicy, &old_mode, old_mask, sizeof(old_mask) * 8, nullptr, 0) != 0) return;
     // MPOL_PREFERRED = 1: fall back to other nodes rather than fail when the node is full
     active = syscall(SYS_set_mempolicy, 1, mask, sizeof(mask) * 8) == 0;
   }
   ~NumaBind() {
-    if (active) syscall(SYS_set_mempolicy, 0 /* MPOL_DEFAULT */, nullptr, 0);
+    if (!active) return;
+    if (old_mode == 0)
+      syscall(SYS_set_mempolicy, 0 /* MPOL_DEFAULT */, nullptr, 0);
+    else
+      syscall(SYS_set_mempolicy, old_mode, old_mask, sizeof(old_mask) * 8);
   }
 };
 
