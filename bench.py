@@ -692,15 +692,22 @@ def main():
     out_pin = Pinned(R * 8)
     ep2 = scratch
 
-    def e2e_models(i, refresh):
+    # A refresh tick (the reference's cadence is one per 50 ms, main.go:39) is charged to EVERY step.
+    # The uploads are the _async entry points: staged into the ctx's pinned blob and enqueued; the
+    # step's blocking schedule call is ordered behind them on the device and is the one
+    # synchronisation of the step (its result is read on the host every step).
+    def e2e_models(i, refresh, block=False):
         if refresh:
-            eng.upload_snapshot(ep2, packed)          # the 50 ms refresh tick, charged to every step
-            eng.upload_models(ep2, pmodels)
+            eng.upload_snapshot(ep2, packed, block=block)
+            eng.upload_models(ep2, pmodels, block=block)
         eng.schedule_models_batch_ptr(ep2, 100 + i, 0, mid_pin[i % 4].data_ptr(), R, mout_pin.data_ptr())
+
+    def e2e_models_blocking(i, refresh):
+        e2e_models(i, refresh, block=True)
 
     def e2e_descr(i, refresh):
         if refresh:
-            eng.upload_snapshot(ep2, packed)
+            eng.upload_snapshot(ep2, packed, block=False)
         eng.schedule_batch_ptr(ep2, 100 + i, req_pin[i % 4].data_ptr(), R, out_pin.data_ptr())
 
     def e2e_rate(fn, refresh):
@@ -716,6 +723,7 @@ def main():
         return R_total * e2e_steps / max_over_ranks(time.perf_counter() - t0)
 
     e2e_value = e2e_rate(e2e_models, True)
+    e2e_blocking = e2e_rate(e2e_models_blocking, True)
     e2e_resident = e2e_rate(e2e_models, False)
     e2e_descr_value = e2e_rate(e2e_descr, True)
     e2e_descr_resident = e2e_rate(e2e_descr, False)
@@ -750,11 +758,14 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT,
                     "h2d_bytes_per_step": 4 * R + nbytes + int(pmodels.target_offsets.nbytes + 8 * pmodels.n_models),
                     "d2h_bytes_per_step": 4 * R, "steps": e2e_steps, "value_snapshot_resident": e2e_resident,
-                    "call": "lig_upload_snapshot + lig_upload_models + lig_schedule_models_batch per step: 4-byte model "
-                            "ids in, 4-byte picks out, the kernel reads / writes the pinned host buffers over PCIe in place",
+                    "value_blocking_uploads": e2e_blocking,
+                    "call": "lig_upload_snapshot_async + lig_upload_models_async + lig_schedule_models_batch (blocking, "
+                            "result read on the host) per step: a refresh tick charged to every step; 4-byte model ids in, "
+                            "4-byte picks out, the kernel reads / writes the pinned host buffers over PCIe in place; "
+                            "value_blocking_uploads = the same with the blocking upload calls (three synchronisations)",
                     "descriptor_call": {"value": e2e_descr_value, "value_snapshot_resident": e2e_descr_resident,
                                         "h2d_bytes_per_step": 16 * R + nbytes, "d2h_bytes_per_step": 8 * R,
-                                        "call": "lig_upload_snapshot + lig_schedule_batch (16-byte descriptors resolved on "
+                                        "call": "lig_upload_snapshot_async + lig_schedule_batch (16-byte descriptors resolved on "
                                                 "the host, 8-byte picks): the round-1 e2e figure"}},
             "gpu_launches": int(launches_per_region),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",

@@ -137,6 +137,15 @@ int lig_pack_snapshot(void* blob, int P, int A, const double* kv, const int32_t*
 int lig_upload_snapshot(lig_ctx* ctx, uint64_t epoch, int P, int A, const double* kv,
                         const int32_t* q, const uint16_t* n_active, const uint16_t* max_active,
                         const uint32_t* bitmap_adapter_major);
+/* The same without waiting for the device: the arrays are copied into the ctx's pinned staging
+ * before the call returns (the caller may reuse them at once), the H2D copy and the table build
+ * are only enqueued.  `epoch` is resident immediately; batches against it are ordered behind the
+ * build on the device, so the refresher goroutine (backend/provider.go:81-88) never blocks on the
+ * GPU and a refresh + the next batch cost one synchronisation, not three.  A device-side failure
+ * of the build surfaces at the next call that synchronises. */
+int lig_upload_snapshot_async(lig_ctx* ctx, uint64_t epoch, int P, int A, const double* kv,
+                              const int32_t* q, const uint16_t* n_active, const uint16_t* max_active,
+                              const uint32_t* bitmap_adapter_major);
 
 /* Delta form of lig_upload_snapshot for the refresh tick (backend/provider.go:134-179 re-scrapes
  * every pod, but between two ticks most pods report the same metrics): `new_epoch` becomes
@@ -284,6 +293,10 @@ typedef struct lig_mpick {
 int lig_upload_models(lig_ctx* ctx, uint64_t epoch, int n_models, const int32_t* target_offsets,
                       const int32_t* target_adapter_ids, const int32_t* target_weights,
                       const uint8_t* critical, const int32_t* self_adapter_ids, const uint8_t* present);
+/* Same, enqueued only (see lig_upload_snapshot_async). */
+int lig_upload_models_async(lig_ctx* ctx, uint64_t epoch, int n_models, const int32_t* target_offsets,
+                            const int32_t* target_adapter_ids, const int32_t* target_weights,
+                            const uint8_t* critical, const int32_t* self_adapter_ids, const uint8_t* present);
 /* Host buffers (page-locked ones are read / written over PCIe in place), blocking. */
 int lig_schedule_models_batch(lig_ctx* ctx, uint64_t epoch, uint64_t seed, uint64_t first_index,
                               const uint32_t* model_ids, int R, lig_mpick* out);

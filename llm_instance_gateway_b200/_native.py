@@ -35,6 +35,7 @@ EXPORTED_SYMBOLS = (
     "lig_comm_allreduce_i32",
     "lig_upload_models", "lig_schedule_models_batch", "lig_schedule_models_batches_device", "lig_resolve_models",
     "lig_pick_kernel_info", "lig_schedule_batch_feedback_device", "lig_update_snapshot",
+    "lig_upload_snapshot_async", "lig_upload_models_async",
 )
 
 
@@ -82,6 +83,7 @@ def load() -> C.CDLL:
     lib.lig_pack_pods.argtypes = [i32, vp, vp, vp, vp, vp, vp]
     lib.lig_pack_snapshot.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp]
     lib.lig_upload_snapshot.argtypes = [vp, u64, i32, i32, vp, vp, vp, vp, vp]
+    lib.lig_upload_snapshot_async.argtypes = [vp, u64, i32, i32, vp, vp, vp, vp, vp]
     lib.lig_upload_snapshot_device.argtypes = [vp, u64, i32, i32, vp, vp]
     lib.lig_schedule_batch.argtypes = [vp, u64, u64, vp, i32, vp]
     lib.lig_schedule_batch_device.argtypes = [vp, u64, u64, vp, i32, vp, vp]
@@ -118,6 +120,7 @@ def load() -> C.CDLL:
     lib.lig_comm_upload_snapshot.argtypes = [vp, u64, i32, i32, vp, vp, vp, vp, vp, i32]
     lib.lig_comm_allreduce_i32.argtypes = [vp, vp, i32, vp]
     lib.lig_upload_models.argtypes = [vp, u64, i32, vp, vp, vp, vp, vp, vp]
+    lib.lig_upload_models_async.argtypes = [vp, u64, i32, vp, vp, vp, vp, vp, vp]
     lib.lig_schedule_models_batch.argtypes = [vp, u64, u64, u64, vp, i32, vp]
     lib.lig_schedule_models_batches_device.argtypes = [vp, u64, u64, u64, vp, i32, vp, i32, vp]
     lib.lig_resolve_models.argtypes = [vp, u64, u64, u64, vp, i32, vp, vp]

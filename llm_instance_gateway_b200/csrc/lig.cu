@@ -1096,15 +1096,21 @@ int lig_get_thresholds(const lig_ctx* c, lig_thresholds* t) {
   return 0;
 }
 
-int lig_upload_snapshot(lig_ctx* c, uint64_t epoch, int P, int A, const double* kv,
-                        const int32_t* q, const uint16_t* na, const uint16_t* ma,
-                        const uint32_t* bitmap) {
+static int upload_snapshot_impl(lig_ctx* c, uint64_t epoch, int P, int A, const double* kv,
+                                const int32_t* q, const uint16_t* na, const uint16_t* ma,
+                                const uint32_t* bitmap, bool synchronise) {
   if (!c) return fail(LIG_ERR_INVALID, "lig_upload_snapshot: ctx is null");
   ligi::SnapshotWrite w;
   if (int rc = ligi::begin_write(c, epoch, P, A, nullptr, true, &w)) return rc;
   // The ctx lock is NOT held from here to the publish: batches against the other resident epoch
   // keep flowing while this one is packed, copied and its tables are built.  The slot's pinned
-  // staging blob is free: the previous upload of this slot synchronised before it returned.
+  // staging blob must be free before the host writes it: an earlier _async upload of this slot
+  // (two epochs ago) may still be copying out of it — wait for that slot's `ready` (a no-op when
+  // it completed long ago, the normal case).
+  if (cudaEventSynchronize(static_cast<Slot*>(w.slot)->ready) != cudaSuccess) {
+    ligi::abort_write(c, &w);
+    return fail(LIG_ERR_CUDA, "an earlier upload of this slot failed: %s", cudaGetErrorString(cudaGetLastError()));
+  }
   int rc = lig_pack_snapshot(w.h_blob, P, A, kv, q, na, ma, bitmap);
   if (!rc && cudaMemcpyAsync(w.d_blob, w.h_blob, w.bytes, cudaMemcpyHostToDevice, w.stream) != cudaSuccess)
     rc = fail(LIG_ERR_CUDA, "snapshot H2D copy failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -1113,7 +1119,17 @@ int lig_upload_snapshot(lig_ctx* c, uint64_t epoch, int P, int A, const double* 
     ligi::abort_write(c, &w);
     return rc;
   }
-  return ligi::finish_write(c, &w, true);
+  return ligi::finish_write(c, &w, synchronise);
+}
+
+int lig_upload_snapshot(lig_ctx* c, uint64_t epoch, int P, int A, const double* kv, const int32_t* q,
+                        const uint16_t* na, const uint16_t* ma, const uint32_t* bitmap) {
+  return upload_snapshot_impl(c, epoch, P, A, kv, q, na, ma, bitmap, true);
+}
+
+int lig_upload_snapshot_async(lig_ctx* c, uint64_t epoch, int P, int A, const double* kv, const int32_t* q,
+                              const uint16_t* na, const uint16_t* ma, const uint32_t* bitmap) {
+  return upload_snapshot_impl(c, epoch, P, A, kv, q, na, ma, bitmap, false);
 }
 
 int lig_update_snapshot(lig_ctx* c, uint64_t new_epoch, uint64_t base_epoch, int n_dirty,
@@ -1418,9 +1434,9 @@ int lig_schedule_scan(lig_ctx* c, uint64_t epoch, uint64_t seed, const lig_req* 
   return 0;
 }
 
-int lig_upload_models(lig_ctx* c, uint64_t epoch, int n_models, const int32_t* off,
-                      const int32_t* tgt_ids, const int32_t* tgt_w, const uint8_t* critical,
-                      const int32_t* self_ids, const uint8_t* present) {
+static int upload_models_impl(lig_ctx* c, uint64_t epoch, int n_models, const int32_t* off,
+                              const int32_t* tgt_ids, const int32_t* tgt_w, const uint8_t* critical,
+                              const int32_t* self_ids, const uint8_t* present, bool synchronise) {
   if (!c || n_models < 0 || (n_models > 0 && (!off || !critical || !self_ids)))
     return fail(LIG_ERR_INVALID, "lig_upload_models: bad argument");
   const int n_rec_in = n_models ? off[n_models] : 0;
@@ -1490,6 +1506,7 @@ int lig_upload_models(lig_ctx* c, uint64_t epoch, int n_models, const int32_t* o
     CUDA_TRY(cudaHostAlloc(&s->h_mtab, cap, cudaHostAllocDefault));
     s->mtab_capacity = cap;
   }
+  CUDA_TRY(cudaEventSynchronize(s->models_ready));   // an earlier _async upload may still read the staging copy
   memset(s->h_mtab, 0, bytes);
   ModelHeader* h = reinterpret_cast<ModelHeader*>(s->h_mtab);
   h->bytes = (uint32_t)bytes;
@@ -1499,7 +1516,7 @@ int lig_upload_models(lig_ctx* c, uint64_t epoch, int n_models, const int32_t* o
   if (!targets.empty()) memcpy(s->h_mtab + sizeof(ModelHeader) + entries.size() * 4, targets.data(), targets.size() * 4);
   CUDA_TRY(cudaMemcpyAsync(s->d_mtab, s->h_mtab, bytes, cudaMemcpyHostToDevice, c->s_up));
   CUDA_TRY(cudaEventRecord(s->models_ready, c->s_up));
-  CUDA_TRY(cudaStreamSynchronize(c->s_up));
+  if (synchronise) CUDA_TRY(cudaStreamSynchronize(c->s_up));
   {
     std::lock_guard<std::mutex> lk(c->mu);
     s->mtab_bytes = (uint32_t)bytes;
@@ -1507,6 +1524,18 @@ int lig_upload_models(lig_ctx* c, uint64_t epoch, int n_models, const int32_t* o
     s->models_valid = s->valid && s->epoch == epoch;
   }
   return 0;
+}
+
+int lig_upload_models(lig_ctx* c, uint64_t epoch, int n_models, const int32_t* off, const int32_t* tgt_ids,
+                      const int32_t* tgt_w, const uint8_t* critical, const int32_t* self_ids,
+                      const uint8_t* present) {
+  return upload_models_impl(c, epoch, n_models, off, tgt_ids, tgt_w, critical, self_ids, present, true);
+}
+
+int lig_upload_models_async(lig_ctx* c, uint64_t epoch, int n_models, const int32_t* off, const int32_t* tgt_ids,
+                            const int32_t* tgt_w, const uint8_t* critical, const int32_t* self_ids,
+                            const uint8_t* present) {
+  return upload_models_impl(c, epoch, n_models, off, tgt_ids, tgt_w, critical, self_ids, present, false);
 }
 
 static int resolve_models_slot(lig_ctx* c, uint64_t epoch, Slot** out) {

@@ -48,10 +48,11 @@ class Engine:
         N.check(self._lib.lig_set_thresholds(self._ctx, C.byref(t)))
 
     # ---- snapshots ----
-    def upload_snapshot(self, epoch: int, snap: PackedSnapshot) -> None:
-        N.check(self._lib.lig_upload_snapshot(self._ctx, epoch, snap.P, snap.A, _ptr(snap.kv),
-                                              _ptr(snap.q), _ptr(snap.n_active),
-                                              _ptr(snap.max_active), _ptr(snap.bitmap)))
+    def upload_snapshot(self, epoch: int, snap: PackedSnapshot, block: bool = True) -> None:
+        """block=False: lig_upload_snapshot_async (staged + enqueued, the device is not waited for)."""
+        fn = self._lib.lig_upload_snapshot if block else self._lib.lig_upload_snapshot_async
+        N.check(fn(self._ctx, epoch, snap.P, snap.A, _ptr(snap.kv), _ptr(snap.q), _ptr(snap.n_active),
+                   _ptr(snap.max_active), _ptr(snap.bitmap)))
 
     def update_snapshot(self, new_epoch: int, base_epoch: int, pod_idx, kv, q, n_active, max_active,
                         adapter_offsets, adapter_ids) -> None:
@@ -88,11 +89,11 @@ class Engine:
         N.check(self._lib.lig_schedule_wait(self._ctx, ticket))
 
     # ---- model requests: the resolve step of HandleRequestBody on the device ----
-    def upload_models(self, epoch: int, models: PackedModels) -> None:
-        N.check(self._lib.lig_upload_models(self._ctx, epoch, models.n_models, _ptr(models.target_offsets),
-                                            _ptr(models.target_adapter_ids), _ptr(models.target_weights),
-                                            _ptr(models.critical), _ptr(models.self_adapter_ids),
-                                            _ptr(models.present)))
+    def upload_models(self, epoch: int, models: PackedModels, block: bool = True) -> None:
+        fn = self._lib.lig_upload_models if block else self._lib.lig_upload_models_async
+        N.check(fn(self._ctx, epoch, models.n_models, _ptr(models.target_offsets),
+                   _ptr(models.target_adapter_ids), _ptr(models.target_weights),
+                   _ptr(models.critical), _ptr(models.self_adapter_ids), _ptr(models.present)))
 
     def schedule_models_batch(self, epoch: int, seed: int, model_ids: np.ndarray, first_index: int = 0,
                               out: Optional[np.ndarray] = None) -> np.ndarray:

@@ -141,3 +141,54 @@ def test_model_table_validation_and_edge_tables(oracle):
         assert ei.value.code == N.LIG_ERR_RANGE
         # a refused upload changes nothing: the previous table keeps serving
         assert np.array_equal(e.schedule_models_batch(1, 3, ids), want)
+
+
+def test_async_uploads_are_ordered_on_the_device(oracle):
+    """lig_upload_snapshot_async / lig_upload_models_async return before the device has copied or
+    built anything; a schedule call issued right behind them must still see exactly that snapshot
+    and model table (device-side ordering), the previous epoch must stay servable, and the pinned
+    staging copies must survive back-to-back async uploads of the same slot."""
+    c = WL.CONFIGS["C3"]
+    R = 20000
+    ids = WL.make_model_requests(R, c["A"], seed=15)
+    reqs = WL.make_requests(R, c["A"], seed=16)
+    models = WL.make_models(c["A"])
+    snaps = [WL.make_snapshot(c["P"], c["A"], seed=300 + i) for i in range(6)]
+    pools = [oracle.Pool(s.pod_records()) for s in snaps]
+    mo = oracle.Models(WL.model_records(models))
+    with Engine(0, max_pods=c["P"], max_adapters=c["A"], max_batch=1 << 16) as e:
+        for i, s in enumerate(snaps):
+            ep = 50 + i
+            e.upload_snapshot(ep, s.packed, block=False)
+            e.upload_models(ep, pack_models(models, s.packed), block=False)
+            got = e.schedule_models_batch(ep, 7 + i, ids, first_index=1000 * i)
+            want = mo.schedule_batch(pools[i], ids, 7 + i, first_index=1000 * i)
+            assert np.array_equal(got, want), i
+            picks = e.schedule_batch(ep, 3, reqs)
+            wantp, _ = pools[i].schedule_batch(s.adapter_names(), WL.UNKNOWN_MODEL, reqs, 3)
+            assert np.array_equal(picks, wantp), i
+            if i:       # the previous epoch is still resident and unchanged
+                prev, _ = pools[i - 1].schedule_batch(snaps[i - 1].adapter_names(), WL.UNKNOWN_MODEL, reqs, 3)
+                assert np.array_equal(e.schedule_batch(ep - 1, 3, reqs), prev), i
+        # the same epoch re-uploaded many times in a row without any synchronising call in between
+        # (each async upload re-stages the slot's pinned blob: the staging guard is what is tested)
+        for k in range(12):
+            s = snaps[k % 6]
+            e.upload_snapshot(99, s.packed, block=False)
+            e.upload_models(99, pack_models(models, s.packed), block=False)
+        last = snaps[11 % 6]
+        got = e.schedule_models_batch(99, 5, ids)
+        assert np.array_equal(got, mo.schedule_batch(pools[11 % 6], ids, 5, first_index=0))
+        # the device queue path right behind an async upload (header not back yet -> strided tables)
+        import torch
+        e.upload_snapshot(101, snaps[2].packed, block=False)
+        d_reqs = torch.from_numpy(reqs.view(np.uint8).reshape(-1)).cuda()
+        d_out = torch.zeros(R * 8, dtype=torch.uint8, device="cuda")
+        torch.cuda.synchronize()
+        st = torch.cuda.Stream()
+        e.upload_snapshot(102, snaps[3].packed, block=False)
+        e.schedule_batches_device(102, 3, [d_reqs.data_ptr()], R, [d_out.data_ptr()], st.cuda_stream)
+        st.synchronize()
+        wantp, _ = pools[3].schedule_batch(snaps[3].adapter_names(), WL.UNKNOWN_MODEL, reqs, 3)
+        from llm_instance_gateway_b200.packer import PICK_DTYPE
+        assert np.array_equal(d_out.cpu().numpy().view(PICK_DTYPE), wantp)
