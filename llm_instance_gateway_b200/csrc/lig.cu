@@ -700,6 +700,13 @@ int begin_write(lig_ctx* c, uint64_t epoch, int P, int A, cudaStream_t stream, b
     w->d_blob = s.d_blob;
     w->h_blob = s.h_blob;
   }
+  if (!rc && own_stream) {
+    // Host-staged writers fill the slot's pinned blob next: an earlier _async upload of this slot
+    // (two epochs ago) may still be copying out of it.  Waiting for the slot's `ready` is a no-op
+    // when that upload completed long ago (the normal case); the ctx lock is not held here.
+    cudaError_t e = cudaEventSynchronize(static_cast<Slot*>(w->slot)->ready);
+    if (e != cudaSuccess) rc = fail(LIG_ERR_CUDA, "an earlier upload of this slot failed: %s", cudaGetErrorString(e));
+  }
   if (rc) {
     c->upload_mu.unlock();
     return rc;
@@ -1104,13 +1111,7 @@ static int upload_snapshot_impl(lig_ctx* c, uint64_t epoch, int P, int A, const 
   if (int rc = ligi::begin_write(c, epoch, P, A, nullptr, true, &w)) return rc;
   // The ctx lock is NOT held from here to the publish: batches against the other resident epoch
   // keep flowing while this one is packed, copied and its tables are built.  The slot's pinned
-  // staging blob must be free before the host writes it: an earlier _async upload of this slot
-  // (two epochs ago) may still be copying out of it — wait for that slot's `ready` (a no-op when
-  // it completed long ago, the normal case).
-  if (cudaEventSynchronize(static_cast<Slot*>(w.slot)->ready) != cudaSuccess) {
-    ligi::abort_write(c, &w);
-    return fail(LIG_ERR_CUDA, "an earlier upload of this slot failed: %s", cudaGetErrorString(cudaGetLastError()));
-  }
+  // staging blob is free: begin_write waited for the slot's previous upload.
   int rc = lig_pack_snapshot(w.h_blob, P, A, kv, q, na, ma, bitmap);
   if (!rc && cudaMemcpyAsync(w.d_blob, w.h_blob, w.bytes, cudaMemcpyHostToDevice, w.stream) != cudaSuccess)
     rc = fail(LIG_ERR_CUDA, "snapshot H2D copy failed: %s", cudaGetErrorString(cudaGetLastError()));
